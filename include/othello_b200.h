@@ -1,0 +1,186 @@
+/*
+ * othello_b200.h -- C ABI of the B200-native batched Othello hot path.
+ *
+ * This is the drop-in boundary for the rules / step-loop / feature / evaluation / learner-
+ * statistics path of ysnrkdm/subproc.  The reference has no native code, so there is no
+ * existing FFI to mirror; each entry point instead names the reference function it replaces
+ * (file:line in the reference tree).  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - bitboards: uint64, bit s = x + 8*y, x = file a..h = 0..7, y = rank 1..8 = 0..7
+ *     (the mask convention of board.py:79 and coord_from_handstr board.py:176-185);
+ *   - colours: 0 Empty, 1 Black, 2 White (board.py:3-7); Black moves first (board.py:26);
+ *   - moves: uint8 square 0..63, 64 = pass ('ps'/'PS', board.py:194), anything else is a hand
+ *     string that does not parse (put_s returns -1);
+ *   - "_host" functions take HOST pointers and run on the context's own stream and workspace;
+ *     all others take DEVICE pointers, launch asynchronously on `stream` (a cudaStream_t passed
+ *     as void*), allocate nothing and keep no global state;
+ *   - every function returns 0 on success, a positive cudaError_t value, or a negative
+ *     OTHELLO_E_* code.  othello_error_string() explains both.
+ */
+#ifndef OTHELLO_B200_H
+#define OTHELLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTHELLO_ABI_VERSION 1
+
+#define OTHELLO_EMPTY 0
+#define OTHELLO_BLACK 1
+#define OTHELLO_WHITE 2
+#define OTHELLO_PASS  64
+
+#define OTHELLO_START_BLACK 0x0000000810000000ull   /* board.py:25 */
+#define OTHELLO_START_WHITE 0x0000001008000000ull   /* board.py:24 */
+
+#define OTHELLO_E_INVALID   (-1)   /* bad argument (null pointer, negative size, depth out of range) */
+#define OTHELLO_E_WORKSPACE (-2)   /* caller-supplied workspace too small */
+#define OTHELLO_E_NO_DEVICE (-3)   /* no CUDA device / driver */
+
+/* step flags (othello_step `flags`, describing the position AFTER the move) */
+#define OTHELLO_F_MUST_PASS 1      /* side to move has no move but the game is not over */
+#define OTHELLO_F_GAME_OVER 2      /* Board.is_game_over(), board.py:57-58 */
+
+/* playout policies: what the two engines behind GameRunner answer to 'go' */
+#define OTHELLO_POLICY_RANDOM 0    /* uniform over puttables(), 'ps' when empty */
+#define OTHELLO_POLICY_GREEDY 1    /* arg-max of the linear evaluation of the successor, ties -> lowest square */
+
+#define OTHELLO_FEATURES   10      /* counts(): discs, mobility, a..h (parameter_progress_position_moves_learn.py:5-17) */
+#define OTHELLO_PHASES      4      /* disc-count shards (0,16),(17,32),(33,48),(49,64) (progress_position_moves_learn.py:112-113) */
+#define OTHELLO_WEIGHTS    10      /* per phase: 9 weights over (mobility, a..h) + intercept */
+#define OTHELLO_STATS     112      /* per phase: XtX[10][10], Xty[10], n, sum y^2 */
+
+int         othello_abi_version(void);
+const char *othello_error_string(int code);
+
+/* ---- rules ---------------------------------------------------------------------------------- */
+
+/* Board.puttables(piece) as a mask (board.py:46-52, via is_puttable_at :141-149 and
+ * hands_for_direc :124-139).  own/opp: discs of `piece` / of the other colour. */
+int othello_legal(const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n, void *stream);
+
+/* Board.put(piece, x, y) without mutation (board.py:161-174): the set of discs that placing
+ * `piece` on `square` flips; 0 when the square is occupied or nothing flips (put returns 0). */
+int othello_flips(const uint64_t *own, const uint64_t *opp, const uint8_t *square, uint64_t *flips,
+                  int64_t n, void *stream);
+
+/* Board.put_s(hand) for the side to move, in place (board.py:192-209), plus the two
+ * is_game_over()/pass checks play_a_turn and the recorders make after it (game_runner.py:162,
+ * game_recorder.py:112).  ret: -1 illegal (state untouched), 0 pass, else number flipped.
+ * flips_out, ret, flags may be NULL. */
+int othello_step(uint64_t *black, uint64_t *white, uint8_t *turn, int32_t *nturn, const uint8_t *move,
+                 uint64_t *flips_out, int32_t *ret, uint8_t *flags, int64_t n, void *stream);
+
+/* n_black / n_white / n_empty (board.py:37-44): out[n][3] */
+int othello_counts(const uint64_t *black, const uint64_t *white, int32_t *out, int64_t n, void *stream);
+
+/* Board.mask_count(color, mask) (board.py:74-81): out[i] = popcount(discs of color[i] & mask[i]) */
+int othello_mask_count(const uint64_t *black, const uint64_t *white, const uint8_t *color, const uint64_t *mask,
+                       int32_t *out, int64_t n, void *stream);
+
+/* ---- features and evaluation ---------------------------------------------------------------- */
+
+/* counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17): out[n][10] =
+ * (64 - empties, mobility(side), popc(side & a) .. popc(side & h)); side = colour 1/2. */
+int othello_features(const uint64_t *black, const uint64_t *white, const uint8_t *side, int32_t *out,
+                     int64_t n, void *stream);
+
+/* Linear phase-weighted evaluation (rows of default_value(),
+ * parameter_progress_position_moves_learn.py:30-36; phase shards progress_position_moves_learn.py:112-113;
+ * the form lr.predict evaluates at :178): out[i] = W[phase][0..8] . (mobility, a..h) + W[phase][9].
+ * weights: DEVICE float[4][10]. */
+int othello_eval(const uint64_t *black, const uint64_t *white, const uint8_t *side, const float *weights,
+                 float *out, int64_t n, void *stream);
+
+/* ---- the game-runner step loop -------------------------------------------------------------- */
+
+/* GameRunner.play_a_game (game_runner.py:165-201) for n_games independent games, one launch.
+ * Game g uses the counter-based RNG stream (seed, gid0 + g); results do not depend on how games
+ * are sharded over launches or GPUs. */
+typedef struct {
+    uint64_t seed;
+    uint64_t gid0;
+    int64_t  n_games;
+    const uint64_t *black0;       /* [n] initial positions, or NULL for the standard opening (board.py:22-27) */
+    const uint64_t *white0;
+    const uint8_t  *turn0;        /* [n] side to move, or NULL = Black */
+    int32_t  policy;              /* OTHELLO_POLICY_* : the engine behind both players */
+    int32_t  random_plies;        /* greedy engine answers uniformly at random while ply < random_plies */
+    int32_t  n_rand_black;        /* go_for's substitution budget n_rand_hands (game_runner.py:116-119,133-152) */
+    int32_t  n_rand_white;
+    const float *weights;         /* DEVICE float[4][10]; required for OTHELLO_POLICY_GREEDY */
+    int32_t  t_max;               /* trajectory capacity in plies (120 holds every game from <= 60 empties) */
+    int64_t  stride;              /* games per trajectory row (>= n_games) */
+    uint64_t *traj_black;         /* [t_max+1][stride] position before ply t (recorder.add, game_runner.py:170,159); NULL = none */
+    uint64_t *traj_white;
+    uint8_t  *traj_move;          /* [t_max][stride] move played at ply t (0..63, 64 = pass) */
+    int32_t  *nplies;             /* [n] plies played, passes included (= nturn of the terminal position) */
+    uint64_t *final_black;        /* [n] terminal position */
+    uint64_t *final_white;
+} othello_playout_args;
+
+int othello_playout(const othello_playout_args *args, void *stream);
+
+/* ---- perft ---------------------------------------------------------------------------------- */
+
+/* Legal-move enumeration to `depth` plies (pass = one ply, a game-over node = one leaf).
+ * Synchronous: expands breadth-first on the device, then one thread per frontier node runs a
+ * depth-first count.  workspace: DEVICE scratch, >= othello_perft_workspace_bytes(depth).
+ * result: HOST pointer. */
+int64_t othello_perft_workspace_bytes(int depth);
+int othello_perft(uint64_t black, uint64_t white, int turn, int depth, void *workspace, int64_t workspace_bytes,
+                  uint64_t *result, void *stream);
+
+/* ---- learner sufficient statistics ---------------------------------------------------------- */
+
+/* For every recorded position t of every game and both sides ('O' = Black then 'X' = White,
+ * progress_position_moves_learn.py:44-47): x = (mobility, a..h, 1), y = (own - opp final discs) *
+ * decay[nplies - t] (:55, decay[k] = 0.9 ** k computed by the host in fp64), accumulated per phase
+ * shard into stats[4][112] (+=): XtX[10][10], Xty[10], n, sum y^2.  stats: DEVICE double, caller zeroes. */
+int othello_learn_accumulate(const uint64_t *traj_black, const uint64_t *traj_white, const int32_t *nplies,
+                             const uint64_t *final_black, const uint64_t *final_white,
+                             int64_t n_games, int64_t stride, int32_t t_max, const double *decay /* [t_max+1] */,
+                             double *stats, void *stream);
+
+/* ---- measurement helper --------------------------------------------------------------------- */
+
+/* INT32 ALU-pipe micro-benchmark: every thread runs `iters` rounds of 8 independent LOP3/SHF
+ * chains (32 integer lane-ops per round).  Used by bench.py to measure the integer roofline
+ * denominator on the box.  sink: DEVICE uint32[blocks*threads]. */
+int othello_int32_peak_kernel(uint32_t *sink, int blocks, int threads, int iters, void *stream);
+
+/* ---- host-buffer front end (what a non-torch caller binds) ----------------------------------- */
+
+typedef struct othello_ctx othello_ctx;
+
+int  othello_ctx_create(int device, othello_ctx **out);
+void othello_ctx_destroy(othello_ctx *ctx);
+
+/* puttables / put_s on host arrays: copies in, launches, copies out, synchronises. */
+int othello_legal_host(othello_ctx *ctx, const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n);
+int othello_step_host(othello_ctx *ctx, uint64_t *black, uint64_t *white, uint8_t *turn, int32_t *nturn,
+                      const uint8_t *move, uint64_t *flips_out, int32_t *ret, uint8_t *flags, int64_t n);
+
+/* play_a_game for n games from host-resident start positions (NULL = standard opening); the
+ * trajectory stays in device memory owned by the context (othello_ctx_trajectory) unless host
+ * trajectory pointers are given.  Per-game results come back to the host arrays. */
+int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t n_games,
+                         const uint64_t *black0, const uint64_t *white0, const uint8_t *turn0,
+                         int32_t policy, int32_t random_plies, int32_t n_rand_black, int32_t n_rand_white,
+                         const float *weights /* host [4][10] or NULL */, int32_t t_max,
+                         uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move /* host or NULL */,
+                         int32_t *nplies, uint64_t *final_black, uint64_t *final_white);
+
+/* device pointers of the last othello_playout_host trajectory ([t_max+1][n], [t_max+1][n], [t_max][n]) */
+int othello_ctx_trajectory(othello_ctx *ctx, uint64_t **traj_black, uint64_t **traj_white, uint8_t **traj_move,
+                           int64_t *stride, int32_t *t_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTHELLO_B200_H */

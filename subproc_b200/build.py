@@ -1,0 +1,48 @@
+"""Build libothello_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m subproc_b200.build [--force]
+
+No torch involved: the library is plain CUDA behind ``extern "C"`` (include/othello_b200.h).
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libothello_b200.so")
+SOURCES = ("rules.cu", "playout.cu", "perft.cu", "learn.cu", "peak.cu", "host_api.cu")
+HEADERS = ("bitboard.cuh", "common.cuh", os.path.join("..", "..", "include", "othello_b200.h"))
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(exe):
+        raise RuntimeError("nvcc not found; cannot build libothello_b200.so")
+    return exe
+
+
+def stale():
+    if not os.path.isfile(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return SO
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
+          [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

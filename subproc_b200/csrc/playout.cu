@@ -1,0 +1,141 @@
+// playout.cu -- GameRunner.play_a_game (game_runner.py:165-201) for millions of games at once.
+//
+// One thread owns one game from the first ply to the last: the position lives in four 32-bit
+// registers pairs (own/opp bitboards), a ply is ~500 integer instructions and touches memory
+// only to append the position and the move to the SoA trajectory [t][game] (a warp writes
+// 32 consecutive u64 = 256 B per array per ply).  The warp runs in lock step; games that end
+// early idle until the longest game of the warp is over.  Nothing is read from HBM after the
+// start position.
+//
+// The loop is the reference's: positions are recorded before every ply and once at the end
+// (recorder.add, game_runner.py:170,159); the side to move asks go_for (game_runner.py:133-152),
+// which may substitute a uniformly random move for the engine's, an engine with no move answers
+// 'ps' and the pass is a ply of its own (board.py:194-195,203-208); the game stops when neither
+// colour can move (board.py:57-58).
+#include "common.cuh"
+
+using namespace ob;
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct Choice { int move; u64 flips; };
+
+// the greedy engine: arg-max over puttables() (ascending square) of the linear evaluation of
+// the successor from the mover's side; strict '>' keeps the lowest square on ties
+__device__ __forceinline__ Choice greedy_choice(u64 legal, u64 own, u64 opp, const float *w_s)
+{
+    Choice best = {-1, 0ull};
+    float best_v = 0.f;
+    for (u64 rem = legal; rem; rem &= rem - 1) {
+        const int s = __ffsll((long long)rem) - 1;
+        const u64 x = 1ull << s;
+        const u64 f = flips_for(x, own, opp);
+        const float v = eval_linear(own | f | x, opp & ~f, w_s);
+        if (best.move < 0 || v > best_v) { best.move = s; best.flips = f; best_v = v; }
+    }
+    return best;
+}
+
+template <bool GREEDY, bool SUBST, bool TRAJ>
+__global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout_args a)
+{
+    __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
+    if (GREEDY) {
+        if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = a.weights[threadIdx.x];
+        __syncthreads();
+    }
+    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (g >= a.n_games) return;
+
+    const u64 b0 = a.black0 ? a.black0[g] : OTHELLO_START_BLACK;
+    const u64 w0 = a.white0 ? a.white0[g] : OTHELLO_START_WHITE;
+    bool black_moves = a.turn0 ? (a.turn0[g] == OTHELLO_BLACK) : true;
+    u64 own = black_moves ? b0 : w0, opp = black_moves ? w0 : b0;
+
+    const u32 key = rng_key(a.seed, a.gid0 + (u64)g);
+    // n_rand_rest = min(n_rand_hands, N_RAND_HAND_UNTIL = 10) (game_runner.py:6,118-119)
+    int rest_b = SUBST ? min(a.n_rand_black, 10) : 0, rest_w = SUBST ? min(a.n_rand_white, 10) : 0;
+
+    u64 *tb = TRAJ ? (u64 *)a.traj_black + g : nullptr;
+    u64 *tw = TRAJ ? (u64 *)a.traj_white + g : nullptr;
+    uint8_t *tm = TRAJ ? a.traj_move + g : nullptr;
+    const int t_max = a.t_max;
+    const int64_t stride = a.stride;
+
+    int t = 0;
+    for (;;) {
+        if (TRAJ && t <= t_max) {
+            __stcs(tb, black_moves ? own : opp);
+            __stcs(tw, black_moves ? opp : own);
+            tb += stride; tw += stride;
+        }
+        const u64 legal = legal_moves(own, opp);
+        int move = OTHELLO_PASS;
+        u64 f = 0, x = 0;
+        if (legal == 0) {
+            if (legal_moves(opp, own) == 0) break;            // is_game_over (board.py:57-58)
+        } else {
+            const int n = __popcll(legal);
+            const u32 r1 = rng_draw(key, (u32)t, 1u);
+            bool random_now = !GREEDY || t < a.random_plies;
+            if (SUBST) {
+                const int rest = black_moves ? rest_b : rest_w;
+                if (rest > 0 && rng_below(rng_draw(key, (u32)t, 0u), (u32)rest) == 0) {   // game_runner.py:134-135
+                    random_now = true;
+                    if (black_moves) rest_b--; else rest_w--;
+                }
+            }
+            if (GREEDY && !random_now) {
+                const Choice c = greedy_choice(legal, own, opp, w_s);
+                move = c.move; f = c.flips; x = 1ull << move;
+            } else {
+                move = kth_set_bit(legal, (int)rng_below(r1, (u32)n));
+                x = 1ull << move;
+                f = flips_for(x, own, opp);
+            }
+        }
+        if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
+        // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
+        const u64 moved = own | f | x;
+        own = opp & ~f;
+        opp = moved;
+        black_moves = !black_moves;
+        t++;
+    }
+    a.nplies[g] = t;
+    a.final_black[g] = black_moves ? own : opp;
+    a.final_white[g] = black_moves ? opp : own;
+}
+
+template <bool GREEDY, bool SUBST>
+int launch(const othello_playout_args &a, cudaStream_t s)
+{
+    const unsigned blocks = ob_blocks(a.n_games, kThreads);
+    if (a.traj_black) playout_kernel<GREEDY, SUBST, true><<<blocks, kThreads, 0, s>>>(a);
+    else playout_kernel<GREEDY, SUBST, false><<<blocks, kThreads, 0, s>>>(a);
+    return ob_launch_status();
+}
+
+}  // namespace
+
+extern "C" int othello_playout(const othello_playout_args *args, void *stream)
+{
+    OB_CHECK_ARGS(args != nullptr);
+    const othello_playout_args &a = *args;
+    OB_CHECK_ARGS(a.n_games >= 0);
+    if (a.n_games == 0) return 0;
+    OB_CHECK_ARGS(a.nplies && a.final_black && a.final_white);
+    OB_CHECK_ARGS((a.black0 == nullptr) == (a.white0 == nullptr));
+    OB_CHECK_ARGS(a.policy == OTHELLO_POLICY_RANDOM || a.policy == OTHELLO_POLICY_GREEDY);
+    OB_CHECK_ARGS(a.policy != OTHELLO_POLICY_GREEDY || a.weights != nullptr);
+    OB_CHECK_ARGS(a.n_rand_black >= 0 && a.n_rand_white >= 0 && a.random_plies >= 0);
+    if (a.traj_black || a.traj_white || a.traj_move)
+        OB_CHECK_ARGS(a.traj_black && a.traj_white && a.traj_move && a.t_max >= 0 && a.stride >= a.n_games);
+    const bool greedy = a.policy == OTHELLO_POLICY_GREEDY;
+    const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (greedy) return subst ? launch<true, true>(a, s) : launch<true, false>(a, s);
+    return subst ? launch<false, true>(a, s) : launch<false, false>(a, s);
+}

@@ -1,0 +1,210 @@
+// rules.cu -- batched Board rules, features and linear evaluation on explicit positions.
+//
+// One thread per position; loads and stores are unit-stride (SoA arrays of u64 / u8 / i32),
+// everything between them is register arithmetic from bitboard.cuh.
+#include "common.cuh"
+
+using namespace ob;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// Board.puttables(piece) (board.py:46-52)
+__global__ void __launch_bounds__(kThreads) legal_kernel(const u64 *__restrict__ own, const u64 *__restrict__ opp,
+                                                         u64 *__restrict__ legal, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) legal[i] = legal_moves(own[i], opp[i]);
+}
+
+// Board.put(piece, x, y) flip set (board.py:161-174)
+__global__ void __launch_bounds__(kThreads) flips_kernel(const u64 *__restrict__ own, const u64 *__restrict__ opp,
+                                                         const uint8_t *__restrict__ square, u64 *__restrict__ flips,
+                                                         int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u64 a = own[i], b = opp[i];
+    const unsigned s = square[i];
+    u64 f = 0;
+    if (s < 64) {
+        const u64 x = 1ull << s;
+        if (!((a | b) & x)) f = flips_for(x, a, b);           // occupied => put returns 0 (board.py:162-163)
+    }
+    flips[i] = f;
+}
+
+// Board.put_s for the side to move (board.py:192-209) + is_game_over of the result (board.py:57-58)
+__global__ void __launch_bounds__(kThreads) step_kernel(u64 *__restrict__ black, u64 *__restrict__ white,
+                                                        uint8_t *__restrict__ turn, int32_t *__restrict__ nturn,
+                                                        const uint8_t *__restrict__ move, u64 *__restrict__ flips_out,
+                                                        int32_t *__restrict__ ret, uint8_t *__restrict__ flags,
+                                                        int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    u64 b = black[i], w = white[i];
+    int t = turn[i];
+    const unsigned mv = move[i];
+    const bool black_moves = (t == OTHELLO_BLACK);
+    u64 own = black_moves ? b : w, opp = black_moves ? w : b;
+    u64 f = 0;
+    int out = -1;
+    if (mv == OTHELLO_PASS) {
+        out = 0;                                              // 'ps'/'PS' is never validated (board.py:194-195)
+    } else if (mv < 64) {
+        const u64 x = 1ull << mv;
+        if (!((own | opp) & x)) f = flips_for(x, own, opp);
+        const int c = __popcll(f);
+        if (c) { out = c; own |= f | x; opp &= ~f; }          // put() == 0 => -1, state untouched (board.py:199-201)
+    }
+    if (out >= 0) {
+        t = black_moves ? OTHELLO_WHITE : OTHELLO_BLACK;
+        b = black_moves ? own : opp;
+        w = black_moves ? opp : own;
+        black[i] = b; white[i] = w;
+        turn[i] = (uint8_t)t;
+        nturn[i] += 1;
+    }
+    if (flips_out) flips_out[i] = f;
+    if (ret) ret[i] = out;
+    if (flags) {
+        const bool bm = (t == OTHELLO_BLACK);
+        const u64 mover = bm ? b : w, other = bm ? w : b;
+        uint8_t fl = 0;
+        if (legal_moves(mover, other) == 0)
+            fl = legal_moves(other, mover) == 0 ? OTHELLO_F_GAME_OVER : OTHELLO_F_MUST_PASS;
+        flags[i] = fl;
+    }
+}
+
+// n_black / n_white / n_empty (board.py:37-44)
+__global__ void __launch_bounds__(kThreads) counts_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
+                                                          int32_t *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u64 b = black[i], w = white[i];
+    out[3 * i + 0] = __popcll(b);
+    out[3 * i + 1] = __popcll(w & ~b);
+    out[3 * i + 2] = 64 - __popcll(b | w);
+}
+
+// Board.mask_count(color, mask) (board.py:74-81)
+__global__ void __launch_bounds__(kThreads) mask_count_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
+                                                              const uint8_t *__restrict__ color,
+                                                              const u64 *__restrict__ mask, int32_t *__restrict__ out,
+                                                              int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u64 b = black[i], w = white[i];
+    const int c = color[i];
+    const u64 discs = c == OTHELLO_BLACK ? b : (c == OTHELLO_WHITE ? w : ~(b | w));
+    out[i] = __popcll(discs & mask[i]);
+}
+
+// counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17)
+__global__ void __launch_bounds__(kThreads) features_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
+                                                            const uint8_t *__restrict__ side, int32_t *__restrict__ out,
+                                                            int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u64 b = black[i], w = white[i];
+    const bool is_black = side[i] == OTHELLO_BLACK;
+    int f[10];
+    features10(is_black ? b : w, is_black ? w : b, f);
+#pragma unroll
+    for (int k = 0; k < 10; k++) out[10 * i + k] = f[k];
+}
+
+// linear phase-weighted evaluation; the 160-byte weight table is staged in shared memory
+__global__ void __launch_bounds__(kThreads) eval_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
+                                                        const uint8_t *__restrict__ side, const float *__restrict__ weights,
+                                                        float *__restrict__ out, int64_t n)
+{
+    __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
+    if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = weights[threadIdx.x];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u64 b = black[i], w = white[i];
+    const bool is_black = side[i] == OTHELLO_BLACK;
+    out[i] = eval_linear(is_black ? b : w, is_black ? w : b, w_s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int othello_legal(const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (own && opp && legal)));
+    if (n == 0) return 0;
+    legal_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)own, (const u64 *)opp,
+                                                                               (u64 *)legal, n);
+    return ob_launch_status();
+}
+
+int othello_flips(const uint64_t *own, const uint64_t *opp, const uint8_t *square, uint64_t *flips, int64_t n,
+                  void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (own && opp && square && flips)));
+    if (n == 0) return 0;
+    flips_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)own, (const u64 *)opp,
+                                                                               square, (u64 *)flips, n);
+    return ob_launch_status();
+}
+
+int othello_step(uint64_t *black, uint64_t *white, uint8_t *turn, int32_t *nturn, const uint8_t *move,
+                 uint64_t *flips_out, int32_t *ret, uint8_t *flags, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && turn && nturn && move)));
+    if (n == 0) return 0;
+    step_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((u64 *)black, (u64 *)white, turn, nturn,
+                                                                              move, (u64 *)flips_out, ret, flags, n);
+    return ob_launch_status();
+}
+
+int othello_counts(const uint64_t *black, const uint64_t *white, int32_t *out, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && out)));
+    if (n == 0) return 0;
+    counts_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black, (const u64 *)white,
+                                                                                out, n);
+    return ob_launch_status();
+}
+
+int othello_mask_count(const uint64_t *black, const uint64_t *white, const uint8_t *color, const uint64_t *mask,
+                       int32_t *out, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && color && mask && out)));
+    if (n == 0) return 0;
+    mask_count_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        (const u64 *)black, (const u64 *)white, color, (const u64 *)mask, out, n);
+    return ob_launch_status();
+}
+
+int othello_features(const uint64_t *black, const uint64_t *white, const uint8_t *side, int32_t *out, int64_t n,
+                     void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && side && out)));
+    if (n == 0) return 0;
+    features_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black,
+                                                                                  (const u64 *)white, side, out, n);
+    return ob_launch_status();
+}
+
+int othello_eval(const uint64_t *black, const uint64_t *white, const uint8_t *side, const float *weights, float *out,
+                 int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && weights && (n == 0 || (black && white && side && out)));
+    if (n == 0) return 0;
+    eval_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black, (const u64 *)white,
+                                                                              side, weights, out, n);
+    return ob_launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Parity of the lock-step playout kernel (GameRunner.play_a_game) and perft on a B200."""
+import numpy as np
+import pytest
+import torch
+
+from subproc_b200 import ops
+from gpu_util import DEV, dev_bits, dev_u8, dev_i32, host_bits, h, sample_positions
+
+pytestmark = pytest.mark.gpu
+
+
+def check_against_oracle(po, ref, n):
+    nplies = po.nplies.cpu().numpy()
+    assert np.array_equal(nplies, ref['nplies'])
+    assert np.array_equal(host_bits(po.final_black), ref['final_black'])
+    assert np.array_equal(host_bits(po.final_white), ref['final_white'])
+    tb, tw, tm = host_bits(po.black), host_bits(po.white), po.move.cpu().numpy()
+    t_idx = np.arange(po.t_max + 1)[:, None]
+    valid_pos = t_idx <= np.minimum(nplies, po.t_max)[None, :]
+    valid_mv = t_idx[:-1] < np.minimum(nplies, po.t_max)[None, :]
+    assert np.array_equal(tb[valid_pos], ref['black'][valid_pos])
+    assert np.array_equal(tw[valid_pos], ref['white'][valid_pos])
+    assert np.array_equal(tm[valid_mv], ref['move'][valid_mv])
+
+
+def test_golden_games_replayed_by_the_kernel(golden_games):
+    """the games the reference's board.py played in oracle/make_golden.py, move for move"""
+    for g in golden_games:
+        w = ops.weights_tensor(np.array(
+            [[100, 99, -1, -1, -1, -1, 3, 8, 20], [75, 99, 2, -5, 7, 6, 4, 5, 5],
+             [25, 99, 2, -5, -7, -6, 4, 5, 5], [1, 100, 50, 30, 30, 30, 30, 30, 30]]), DEV)
+        po = ops.playout(1, seed=g['seed'], gid0=g['gid'], device=DEV, policy=g['policy'],
+                         random_plies=g['random_plies'], n_rand_black=g['n_rand_black'],
+                         n_rand_white=g['n_rand_white'], weights=w)
+        n = len(g['plies'])
+        assert int(po.nplies.cpu()[0]) == n
+        assert po.move[:n, 0].cpu().tolist() == [p['move'] for p in g['plies']]
+        assert host_bits(po.black[:n + 1, 0].contiguous()).tolist() == [h(p['b']) for p in g['positions']]
+        assert host_bits(po.white[:n + 1, 0].contiguous()).tolist() == [h(p['w']) for p in g['positions']]
+
+
+def test_random_playouts_bit_exact(oracle):
+    n = 4096 + 37                                      # ragged: not a multiple of the block size
+    po = ops.playout(n, seed=1, gid0=0, device=DEV)
+    check_against_oracle(po, oracle.playout(1, 0, n), n)
+    assert 55 < po.nplies.float().mean().item() < 65
+
+
+def test_substitution_rule_and_greedy_bit_exact(oracle):
+    w = torch.from_numpy(oracle.DEFAULT_WEIGHTS.astype(np.float32)).to(DEV)
+    n = 700
+    po = ops.playout(n, seed=5, gid0=100, device=DEV, n_rand_black=3, n_rand_white=10)
+    check_against_oracle(po, oracle.playout(5, 100, n, n_rand_black=3, n_rand_white=10), n)
+    po = ops.playout(n, seed=6, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, random_plies=10, weights=w)
+    check_against_oracle(po, oracle.playout(6, 0, n, policy=1, random_plies=10), n)
+    po = ops.playout(n, seed=7, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, n_rand_black=10, n_rand_white=2, weights=w)
+    check_against_oracle(po, oracle.playout(7, 0, n, policy=1, n_rand_black=10, n_rand_white=2), n)
+
+
+def test_custom_start_positions_and_turns(oracle):
+    b, w = sample_positions(oracle, 40, seed=41, stride=3)
+    n = b.size
+    turn = (np.arange(n) % 2 + 1).astype(np.uint8)
+    po = ops.playout(n, seed=9, gid0=7, device=DEV, black0=dev_bits(b), white0=dev_bits(w), turn0=dev_u8(turn))
+    check_against_oracle(po, oracle.playout(9, 7, n, black0=b, white0=w, turn0=turn), n)
+
+
+def test_sharding_invariance_and_no_trajectory_mode(oracle):
+    """game g depends only on (seed, gid): any split over launches / GPUs gives the same games"""
+    n = 3000
+    whole = ops.playout(n, seed=3, gid0=0, device=DEV)
+    a = ops.playout(1000, seed=3, gid0=0, device=DEV)
+    b = ops.playout(2000, seed=3, gid0=1000, device=DEV, trajectory=False)
+    assert torch.equal(whole.nplies, torch.cat([a.nplies, b.nplies]))
+    assert torch.equal(whole.final_black, torch.cat([a.final_black, b.final_black]))
+    assert torch.equal(whole.final_white, torch.cat([a.final_white, b.final_white]))
+    assert torch.equal(whole.move[:60, :1000], a.move[:60])
+    assert b.black is None
+
+
+def test_truncated_trajectory_capacity(oracle):
+    n = 500
+    po = ops.playout(n, seed=2, gid0=0, device=DEV, t_max=20)
+    ref = oracle.playout(2, 0, n, t_max=20)
+    check_against_oracle(po, ref, n)
+    assert (po.nplies > 20).all()
+
+
+def test_million_games_round_trip_properties():
+    """BASELINE config 3 at full size: every recorded ply, replayed through the step kernel, must
+    reproduce the next recorded position; finals are terminal; disc counts are consistent."""
+    n = 1 << 20
+    po = ops.playout(n, seed=1, gid0=0, device=DEV)
+    nplies = po.nplies
+    assert int(nplies.min()) >= 9 and int(nplies.max()) <= 120
+    total = po.total_positions()
+    assert 60.0 < total / n < 61.0
+    fin = ops.legal(po.final_black, po.final_white) | ops.legal(po.final_white, po.final_black)
+    assert int((fin != 0).sum()) == 0                                  # finals are game-over positions
+    c = po.final_counts()
+    assert int((c.sum(dim=1) != 64).sum()) == 0 and int(c[:, 2].max()) <= 60
+    turn = torch.ones(n, dtype=torch.uint8, device=DEV)
+    nturn = torch.zeros(n, dtype=torch.int32, device=DEV)
+    for t in (0, 1, 7, 30, 52, 58, 59, 60, 61):
+        live = nplies > t
+        b, w = po.black[t].clone(), po.white[t].clone()
+        turn.fill_(1 if t % 2 == 0 else 2)
+        nturn.fill_(t)
+        _, ret, _ = ops.step(b, w, turn, nturn, po.move[t].contiguous())
+        assert int((ret[live] < 0).sum()) == 0
+        assert torch.equal(b[live], po.black[t + 1][live]) and torch.equal(w[live], po.white[t + 1][live])
+    last_b = po.black.gather(0, nplies.long()[None, :])[0]
+    assert torch.equal(last_b, po.final_black)
+
+
+def test_perft_known_answers(oracle):
+    want = [1, 4, 12, 56, 244, 1396, 8200, 55092, 390216, 3005288, 24571284]
+    for d, v in enumerate(want):
+        assert ops.perft(d, device=DEV) == v, d
+
+
+def test_perft_other_roots_against_oracle(oracle):
+    b, w = sample_positions(oracle, 6, seed=77, stride=9)
+    for i in range(0, b.size, 2):
+        for turn in (1, 2):
+            for d in (1, 2, 4):
+                assert ops.perft(d, int(b[i]), int(w[i]), turn, device=DEV) == oracle.perft(d, int(b[i]), int(w[i]), turn)
