@@ -136,57 +136,67 @@ def run_reference_arm(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """samples nvidia-smi clocks / throttle reasons every 100 ms while the timed region runs"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """samples SM clock and throttle reasons through NVML in a thread WHILE the timed region runs
+    (the region lasts tens of ms, too short for `nvidia-smi -lms`); same fields as the recipe's
+    nvidia-smi line: clocks.sm, clocks.max.sm, clocks_event_reasons.*"""
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
-        self.lines = []
-        self.proc = None
+    def __init__(self, cuda_index):
+        self.cuda_index = cuda_index
+        self.samples = []
+        self.reasons = 0
+        self.max_mhz = None
+        self.handle = None
+        self.err = None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.cuda_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._sample()
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:                       # pragma: no cover - depends on the box
+            self.err = "%s: %s" % (type(e).__name__, e)
+            self.handle = None
+
+    def _sample(self):
+        nv = self.nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        self.reasons |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap),
+                 ("hw_power_brake", nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown)]
+        reasons = [n for n, bit in names if self.reasons & bit]
+        sm = sorted(self.samples[1:] or self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "how": "NVML SM clock + throttle reasons polled every ~1 ms during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -346,7 +356,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU per step")
