@@ -278,6 +278,40 @@ def make_probe(ns, games, n_positions=160):
     return out
 
 
+def make_paramgen():
+    """paramgen.write_data (paramgen.py:5-19) run on a few parameter tuples.  paramgen.py needs its
+    py2 print statements parenthesised and a stub for its ``import config``; nothing else changes."""
+    import re
+    import tempfile
+    import types
+    from . import build_ref
+    path = os.path.join(build_ref.REF_SRC, "paramgen.py")
+    text = open(path).read()
+    text = re.sub(r"^(\s*)print (.*)$", r"\1print(\2)", text, flags=re.M)
+    sys.modules.setdefault("config", types.ModuleType("config"))
+    mod = types.ModuleType("paramgen_ref")
+    exec(compile(text, path, "exec"), mod.__dict__)
+    cases = []
+    rng = np.random.RandomState(11)
+    params = [
+        (2, 100, 99, -1, -1, -1, -1, 3, 8, 20, 75, 99, 2, -5, 7, 6, 4, 5, 5, 25, 99, 2, -5, -7, -6, 4, 5, 5,
+         1, 100, 50, 30, 30, 30, 30, 30, 30),
+        tuple([3] + [int(v) for v in rng.randint(-127, 128, size=36)]),
+        tuple([2] + [-127, 127, 0, -1, 1] + [0] * 31),
+    ]
+    for p in params:
+        with tempfile.NamedTemporaryFile(delete=False) as f:
+            name = f.name
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.write_data(name, p)
+        data = open(name, "rb").read()
+        os.unlink(name)
+        cases.append({'params': list(p), 'bytes': data.hex()})
+    return cases
+
+
 def dump(name, obj):
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name)
@@ -304,6 +338,7 @@ def main():
         games.append(play_game(ns, 3, gid, 1, 0, 10, 2, rows, record_features=False))
     dump("games.json.gz", games)
     dump("probe.json.gz", make_probe(ns, games))
+    dump("paramgen.json.gz", make_paramgen())
     n_pass = sum(1 for g in games for p in g['plies'] if p['move'] == 64)
     print("games=%d plies=%d passes=%d" % (len(games), sum(len(g['plies']) for g in games), n_pass))
     return 0

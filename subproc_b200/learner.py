@@ -1,0 +1,177 @@
+"""The data-parallel learner: per-phase linear regression from statistics accumulated on the GPUs.
+
+Replaces, for BASELINE config 5, the reference's learning round trip
+(progress_position_moves_learn.py): every position of every self-play game contributes its
+``counts()`` features and its discounted final score (``__update_state_for_a_book`` :37-48,
+``l = 0.90`` :24) to the normal equations of its disc-count shard (:112-113); where the reference
+enqueues four pyres jobs and polls Redis for their answers (:115-158), the ranks here exchange ONE
+all-reduce of 4 x 112 doubles and every rank solves the four 10 x 10 systems itself.
+
+What is kept from the reference, to the letter:
+  * the regressors (mobility, a..h) + intercept -- ``LinearRegression(fit_intercept=True)`` (:167);
+    rank-deficient shards (square classes nobody occupies yet) get sklearn's minimum-norm solution;
+  * ``param = coef * 127 / max|coef|`` with the intercept dropped (:180-181);
+  * ``int(x)`` truncation toward zero when the parameters are stored (:196-203), the field order
+    'A'.. and the ``(header, w0..w35)`` tuple of ``read_parameters`` (:211-224).
+What differs, and why: the reference fits on <= 50 000 keys drawn from its smoothed value table with
+Python's ``random`` and ``sklearn.utils.resample`` (:66-86,160-165) -- unpinned RNG, no test in the
+reference fixes any output -- so this path regresses on the full sample stream instead (every
+position once per side).  The order-dependent table itself is ``subproc_b200.value_table``.
+"""
+import math
+
+import numpy as np
+
+from . import parameter as parameter_mod
+
+PHASE_SHARDS = [(0, 16), (17, 32), (33, 48), (49, 64)]        # progress_position_moves_learn.py:112-113
+N_X = 10                                                        # mobility, a..h, intercept
+N_STATS = 112                                                   # XtX[10][10], Xty[10], n, sum y^2
+
+
+def unpack_stats(row):
+    row = np.asarray(row, dtype=np.float64)
+    return row[:100].reshape(10, 10), row[100:110], float(row[110]), float(row[111])
+
+
+def solve_shard(row, rcond=1e-12):
+    """OLS with intercept from one shard's statistics; minimum-norm when the Gram matrix is singular
+    (what sklearn's lstsq-based LinearRegression returns).  -> dict(coef[9], intercept, rmse, r2, n)"""
+    xtx, xty, n, syy = unpack_stats(row)
+    if n <= 0:
+        return dict(coef=np.zeros(9), intercept=0.0, rmse=float('nan'), r2=float('nan'), n=0)
+    xbar = xtx[:9, 9] / n                                       # column of ones: sum x_i
+    ybar = xty[9] / n
+    sxx = xtx[:9, :9] - n * np.outer(xbar, xbar)                # centred Gram matrix
+    sxy = xty[:9] - n * xbar * ybar
+    coef = np.zeros(9)
+    live = np.flatnonzero(np.diag(sxx) > 0)                     # constant columns (e.g. classes nobody owns yet) get 0
+    if live.size:
+        sub = sxx[np.ix_(live, live)]
+        lam, q = np.linalg.eigh((sub + sub.T) * 0.5)
+        keep = lam > rcond * max(lam.max(), 0.0)
+        inv = np.zeros_like(lam)
+        inv[keep] = 1.0 / lam[keep]
+        coef[live] = q @ (inv * (q.T @ sxy[live]))
+    intercept = ybar - float(xbar @ coef)
+    w = np.concatenate([coef, [intercept]])
+    sse = max(syy - 2.0 * float(w @ xty) + float(w @ xtx @ w), 0.0)
+    sst = syy - n * ybar * ybar
+    return dict(coef=coef, intercept=intercept, rmse=math.sqrt(sse / n),
+                r2=(1.0 - sse / sst) if sst > 0 else float('nan'), n=int(n))
+
+
+def fit_from_stats(stats):
+    """stats [4][112] (numpy or tensor) -> list of 4 shard fits."""
+    if hasattr(stats, "detach"):
+        stats = stats.detach().cpu().numpy()
+    return [solve_shard(stats[s]) for s in range(4)]
+
+
+def scale_param(coef):
+    """coef * 127 / max|coef| (progress_position_moves_learn.py:180-181)"""
+    m = float(np.max(np.abs(coef)))
+    if m == 0.0:
+        return tuple(0.0 for _ in coef)
+    k = 127 / m
+    return tuple(float(c) * k for c in coef)
+
+
+def stored_parameters(params_rows):
+    """__store_parameters: flatten the 4 rows, int() truncation toward zero (:196-203)"""
+    return [int(x) for row in params_rows for x in row]
+
+
+def allreduce_stats(stats):
+    """sum the per-rank statistics over all ranks (NCCL for CUDA tensors, gloo for CPU tensors).
+    A no-op in a single process."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def shard_of_games(total_games, rank, world):
+    """contiguous split of global game ids: rank r plays [lo, hi) -- g // (B / ngpu) of SURVEY 8(e)"""
+    per = (total_games + world - 1) // world
+    lo = min(rank * per, total_games)
+    return lo, min(lo + per, total_games)
+
+
+class ProgressPositionMovesLearn(object):
+    """The reference learner's public surface (name / configure / fit_parameter / read_parameters,
+    learn_base.py:8-33, progress_position_moves_learn.py:19-35) over on-GPU self-play."""
+
+    def __init__(self):
+        self.conf = {}
+        self.a = 0.03
+        self.b = 0.003
+        self.l = 0.90
+        self.parameter = parameter_mod.ProgressPositionMovesParameter()
+        self.params = None                      # stored ints, flat list of 36
+        self.last_fits = None
+        self.last_stats = None
+        self.last_processed_id = -1
+
+    def name(self):
+        return 'progresspositionmovelearn'
+
+    def configure(self, conf_dict):
+        self.conf = conf_dict
+        self.parameter.configure(conf_dict)
+
+    def last_processed(self):
+        return self.last_processed_id
+
+    def read_parameters(self):
+        """(header, w0..w35) (:211-224); the default rows until something has been learnt"""
+        if self.params is None:
+            self.params = stored_parameters(self.parameter.default_value())
+        return tuple([self.parameter.header()] + list(self.params))
+
+    def weights_table(self):
+        return self.parameter.weights_table(self.read_parameters())
+
+    # ---- one learning iteration ------------------------------------------------------------
+    def accumulate(self, playout, stats=None):
+        from . import ops
+        return ops.learn_accumulate(playout, stats=stats, lam=self.l)
+
+    def fit_parameter(self, phase_from, phase_to):
+        """(mse, score, param, nsample) of one shard, like the reference's worker job (:160-184),
+        from the statistics of the last iteration."""
+        s = PHASE_SHARDS.index((phase_from, phase_to))
+        fit = self.last_fits[s]
+        return fit['rmse'], fit['r2'], scale_param(fit['coef']), fit['n']
+
+    def learn_from_stats(self, stats, book_id=None):
+        """all-reduce -> 4 solves -> scale to +-127 -> int() -> stored parameters"""
+        stats = allreduce_stats(stats)
+        self.last_stats = stats
+        self.last_fits = fit_from_stats(stats)
+        rows = []
+        old = np.asarray(self.read_parameters()[1:], dtype=np.float64).reshape(4, 9)
+        for s, (lo, hi) in enumerate(PHASE_SHARDS):
+            if self.last_fits[s]['n'] > 0:
+                rows.append(self.fit_parameter(lo, hi)[2])
+            else:
+                rows.append(tuple(old[s]))
+        self.params = stored_parameters(rows)
+        if book_id is not None:
+            self.last_processed_id = book_id
+        return rows
+
+    def self_play_iteration(self, games_per_rank, seed=0, iteration=0, random_plies=10, device=None, rank=0,
+                            world=1, t_max=120):
+        """config 5: greedy self-play with the current weights on this rank's shard of game ids,
+        statistics, all-reduce, refit.  Returns (playout, new parameter rows)."""
+        import torch
+        from . import ops
+        dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        w = torch.from_numpy(self.weights_table()).to(dev)
+        gid0 = (iteration * world + rank) * games_per_rank
+        po = ops.playout(games_per_rank, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
+                         random_plies=random_plies, weights=w, t_max=t_max)
+        stats = self.accumulate(po)
+        rows = self.learn_from_stats(stats, book_id=gid0 + games_per_rank - 1)
+        return po, rows
