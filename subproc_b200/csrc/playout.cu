@@ -13,6 +13,7 @@
 // 'ps' and the pass is a ply of its own (board.py:194-195,203-208); the game stops when neither
 // colour can move (board.py:57-58).
 #include "common.cuh"
+#include "fastboard.cuh"
 
 using namespace ob;
 
@@ -22,17 +23,42 @@ constexpr int kThreads = 128;
 
 struct Choice { int move; u64 flips; };
 
+// ray masks for obf::flips_for, [direction][square] so that lanes with different squares spread
+// over the shared-memory banks (2 KB per CTA)
+struct Rays {
+    const u64 *t;
+    __device__ __forceinline__ u64 operator()(int d, int s) const { return t[d * 64 + s]; }
+};
+
+__device__ __forceinline__ void fill_rays(u64 *t)
+{
+    for (int i = threadIdx.x; i < obf::kRayDirs * 64; i += blockDim.x) t[i] = obf::make_ray(i >> 6, i & 63);
+}
+
+// w[phase] . (mobility, a..h) + w[phase][9] with the tuned move generator
+__device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__restrict__ w)
+{
+    const int discs = __popcll(own | opp);
+    const float *row = w + 10 * phase_row(discs);
+    float acc = row[9];
+    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)__popcll(own & kClassMask[k]), acc);
+    return acc;
+}
+
 // the greedy engine: arg-max over puttables() (ascending square) of the linear evaluation of
 // the successor from the mover's side; strict '>' keeps the lowest square on ties
-__device__ __forceinline__ Choice greedy_choice(u64 legal, u64 own, u64 opp, const float *w_s)
+__device__ __forceinline__ Choice greedy_choice(u64 legal, u64 own, u64 opp, u64 own_r, u64 opp_r, const Rays &rays,
+                                                const float *w_s)
 {
     Choice best = {-1, 0ull};
     float best_v = 0.f;
     for (u64 rem = legal; rem; rem &= rem - 1) {
         const int s = __ffsll((long long)rem) - 1;
         const u64 x = 1ull << s;
-        const u64 f = flips_for(x, own, opp);
-        const float v = eval_linear(own | f | x, opp & ~f, w_s);
+        const u64 f = obf::flips_for(s, own, opp, own_r, opp_r, rays);
+        const float v = eval_fast(own | f | x, opp & ~f, w_s);
         if (best.move < 0 || v > best_v) { best.move = s; best.flips = f; best_v = v; }
     }
     return best;
@@ -42,10 +68,13 @@ template <bool GREEDY, bool SUBST, bool TRAJ>
 __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout_args a)
 {
     __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
     if (GREEDY) {
         if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = a.weights[threadIdx.x];
-        __syncthreads();
     }
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
     const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (g >= a.n_games) return;
 
@@ -71,11 +100,12 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
             __stcs(tw, black_moves ? opp : own);
             tb += stride; tw += stride;
         }
-        const u64 legal = legal_moves(own, opp);
+        const u64 own_r = obf::rev64(own), opp_r = obf::rev64(opp);
+        const u64 legal = obf::legal_moves(own, opp, own_r, opp_r);
         int move = OTHELLO_PASS;
         u64 f = 0, x = 0;
         if (legal == 0) {
-            if (legal_moves(opp, own) == 0) break;            // is_game_over (board.py:57-58)
+            if (obf::legal_moves(opp, own, opp_r, own_r) == 0) break;   // is_game_over (board.py:57-58)
         } else {
             const int n = __popcll(legal);
             const u32 r1 = rng_draw(key, (u32)t, 1u);
@@ -88,12 +118,12 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
                 }
             }
             if (GREEDY && !random_now) {
-                const Choice c = greedy_choice(legal, own, opp, w_s);
+                const Choice c = greedy_choice(legal, own, opp, own_r, opp_r, rays, w_s);
                 move = c.move; f = c.flips; x = 1ull << move;
             } else {
                 move = kth_set_bit(legal, (int)rng_below(r1, (u32)n));
                 x = 1ull << move;
-                f = flips_for(x, own, opp);
+                f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
             }
         }
         if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }

@@ -1,0 +1,30 @@
+// tests/fastboard_host.cpp -- TEST SCAFFOLDING: compiles subproc_b200/csrc/fastboard.cuh for the
+// host so the exact source the kernels use can be compared with the oracle without a GPU.
+#include "../subproc_b200/csrc/fastboard.cuh"
+
+static unsigned long long g_rays[4][64];
+static bool g_init = false;
+struct Rays { unsigned long long operator()(int d, int s) const { return g_rays[d][s]; } };
+
+static void init()
+{
+    if (g_init) return;
+    for (int d = 0; d < 4; d++) for (int s = 0; s < 64; s++) g_rays[d][s] = obf::make_ray(d, s);
+    g_init = true;
+}
+
+extern "C" void fb_legal(const unsigned long long *own, const unsigned long long *opp, unsigned long long *out, long n)
+{
+    for (long i = 0; i < n; i++) out[i] = obf::legal_moves(own[i], opp[i]);
+}
+
+extern "C" void fb_flips(const unsigned long long *own, const unsigned long long *opp, const unsigned char *sq,
+                         unsigned long long *out, long n)
+{
+    init();
+    for (long i = 0; i < n; i++) {
+        const unsigned long long x = 1ull << sq[i];
+        out[i] = ((own[i] | opp[i]) & x) ? 0ull
+                 : obf::flips_for(sq[i], own[i], opp[i], obf::rev64(own[i]), obf::rev64(opp[i]), Rays());
+    }
+}

@@ -1,0 +1,59 @@
+"""The tuned rules primitives (csrc/fastboard.cuh: all-left floods on the board and its 180-degree
+rotation, carry-propagation rows and rays) compiled for the HOST and compared with the oracle.
+Same source as the kernels, so algorithmic slips are caught on the CPU box."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "fastboard_host.so")
+
+
+@pytest.fixture(scope="module")
+def fb():
+    src = os.path.join(HERE, "fastboard_host.cpp")
+    hdr = os.path.join(HERE, "..", "subproc_b200", "csrc", "fastboard.cuh")
+    if not os.path.isfile(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
+    return ctypes.CDLL(SO)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def positions(oracle, n_games, seed):
+    r = oracle.playout(seed, 0, n_games)
+    bs, ws = [], []
+    for g in range(n_games):
+        n = int(r['nplies'][g])
+        bs.append(r['black'][:n + 1, g])
+        ws.append(r['white'][:n + 1, g])
+    return np.concatenate(bs), np.concatenate(ws)
+
+
+def test_fast_legal_and_flips_match_oracle(fb, oracle):
+    b, w = positions(oracle, 500, 51)
+    rng = np.random.RandomState(1)
+    n = b.size
+    occ = rng.randint(0, 2 ** 62, size=20000).astype(np.uint64) | (rng.randint(0, 4, size=20000).astype(np.uint64) << np.uint64(62))
+    col = rng.randint(0, 2 ** 62, size=20000).astype(np.uint64) | (rng.randint(0, 4, size=20000).astype(np.uint64) << np.uint64(62))
+    b = np.ascontiguousarray(np.concatenate([b, occ & col]))
+    w = np.ascontiguousarray(np.concatenate([w, occ & ~col]))
+    n = b.size
+    out = np.zeros(n, dtype=np.uint64)
+    for own, opp, piece in ((b, w, 1), (w, b, 2)):
+        fb.fb_legal(P(own), P(opp), P(out), ctypes.c_long(n))
+        assert np.array_equal(out, oracle.puttables(b, w, piece))
+        sq = rng.randint(0, 64, size=n).astype(np.uint8)
+        legal = oracle.puttables(b, w, piece)
+        for i in range(0, n, 3):                         # bias a third of the squares towards legal moves
+            if legal[i]:
+                bits = [s for s in range(64) if (int(legal[i]) >> s) & 1]
+                sq[i] = bits[rng.randint(len(bits))]
+        fb.fb_flips(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
+        _, _, want, _ = oracle.put(b, w, piece, sq)
+        assert np.array_equal(out, want)
