@@ -1,0 +1,176 @@
+// greedy.cu -- greedy self-play (BASELINE config 4): GameRunner.play_a_game where the engine behind
+// both players answers 'go' with the arg-max, over puttables(), of the linear evaluation of the
+// successor position from the mover's side (ties -> lowest square).
+//
+// A lane owns a game, but the expensive part -- one flip + one move generation + one evaluation
+// per CHILD, ~9.5 children per position, 1..33 per game -- is flattened over the warp: every ply
+// the 32 games of a warp publish their positions and enumerate their (game, square) work items
+// into shared memory; the warp then evaluates 32 items per round, whatever game they belong to,
+// and reduces per game with two native 32-bit shared-memory atomics (ATOMS.MAX on the order-
+// preserving bits of the score, ATOMS.MIN on the square among the lanes that hold the maximum).
+// This keeps the lanes ~90 % busy; one-thread-per-game loops run at the pace of the warp's
+// largest move list (~45 % busy).  Weight rows and ray masks are staged in shared memory.
+//
+// go_for's substitution rule (game_runner.py:133-152) and the `random_plies` opening are decided
+// per lane exactly as in the oracle; such plies and forced moves (one legal move) skip evaluation.
+#include "playout_common.cuh"
+
+using namespace ob;
+using namespace obp;
+
+namespace {
+
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxItems = 32 * 33 + 32;       // a position has at most 33 legal moves
+constexpr unsigned kFull = 0xffffffffu;
+
+struct WarpScratch {
+    u64 own[32], opp[32];                     // positions of the 32 games (mover-relative)
+    unsigned best_key[32];                    // arg-max state per game
+    unsigned best_sq[32];
+    unsigned short item[kMaxItems];           // (game lane << 8) | square
+};
+
+// order-preserving map float -> u32 (larger float <=> larger unsigned); -0.0 is folded into +0.0
+__device__ __forceinline__ unsigned ordered_bits(float v)
+{
+    const unsigned u = __float_as_uint(v + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <bool SUBST, bool TRAJ>
+__global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_args a)
+{
+    __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    __shared__ WarpScratch scratch[kWarps];
+    if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = a.weights[threadIdx.x];
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
+    WarpScratch &ws = scratch[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+
+    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool done = g >= a.n_games;                               // lanes past the batch only help evaluating
+    const int64_t gi = done ? 0 : g;
+    const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
+    const u64 w0 = a.white0 ? a.white0[gi] : OTHELLO_START_WHITE;
+    bool black_moves = a.turn0 ? (a.turn0[gi] == OTHELLO_BLACK) : true;
+    u64 own = black_moves ? b0 : w0, opp = black_moves ? w0 : b0;
+    const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
+    // n_rand_rest = min(n_rand_hands, N_RAND_HAND_UNTIL = 10) (game_runner.py:6,118-119)
+    int rest_b = SUBST ? min(a.n_rand_black, 10) : 0, rest_w = SUBST ? min(a.n_rand_white, 10) : 0;
+
+    u64 *tb = TRAJ ? (u64 *)a.traj_black + gi : nullptr;
+    u64 *tw = TRAJ ? (u64 *)a.traj_white + gi : nullptr;
+    uint8_t *tm = TRAJ ? a.traj_move + gi : nullptr;
+    const int t_max = a.t_max;
+    const int64_t stride = a.stride;
+
+    int t = 0;
+    while (__any_sync(kFull, !done)) {
+        u64 legal = 0, own_r = 0, opp_r = 0;
+        if (!done) {
+            if (TRAJ && t <= t_max) {
+                __stcs(tb, black_moves ? own : opp);
+                __stcs(tw, black_moves ? opp : own);
+                tb += stride; tw += stride;
+            }
+            own_r = obf::rev64(own); opp_r = obf::rev64(opp);
+            legal = obf::legal_moves(own, opp, own_r, opp_r);
+            if (legal == 0 && obf::legal_moves(opp, own, opp_r, own_r) == 0) {     // is_game_over (board.py:57-58)
+                done = true;
+                a.nplies[g] = t;
+                a.final_black[g] = black_moves ? own : opp;
+                a.final_white[g] = black_moves ? opp : own;
+            }
+        }
+        const bool moving = !done && legal != 0;              // otherwise: finished, or this ply is a pass
+        const int n = __popcll(legal);
+        bool random_now = t < a.random_plies;
+        if (SUBST && moving) {
+            if (substitute_now(key, t, black_moves ? rest_b : rest_w)) {           // game_runner.py:134-150
+                random_now = true;
+                if (black_moves) rest_b--; else rest_w--;
+            }
+        }
+        const bool evaluate = moving && !random_now && n > 1;  // a forced move needs no evaluation
+        // exclusive prefix of the children counts over the warp
+        const int cnt = evaluate ? n : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        if (total > 0) {
+            ws.own[lane] = own; ws.opp[lane] = opp;
+            ws.best_key[lane] = 0u; ws.best_sq[lane] = 64u;
+            if (evaluate) {
+                int idx = incl - cnt;
+                for (u64 rem = legal; rem; rem &= rem - 1)
+                    ws.item[idx++] = (unsigned short)((lane << 8) | (__ffsll((long long)rem) - 1));
+            }
+            __syncwarp();
+            for (int base = 0; base < total; base += 32) {
+                const int j = base + lane;
+                const bool have = j < total;
+                unsigned owner = 0, sq = 0, kbits = 0, before = 0;
+                if (have) {
+                    const unsigned it = ws.item[j];
+                    owner = it >> 8; sq = it & 63u;
+                    const u64 o = ws.own[owner], p = ws.opp[owner];
+                    const u64 f = obf::flips_for((int)sq, o, p, obf::rev64(o), obf::rev64(p), rays);
+                    kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, w_s));
+                    before = ws.best_key[owner];
+                }
+                __syncwarp();
+                if (have) atomicMax(&ws.best_key[owner], kbits);
+                __syncwarp();
+                // lanes that raised their game's maximum in this round restart its square, then the
+                // lowest square among the lanes holding the maximum wins (items ascend with the square)
+                const bool top = have && ws.best_key[owner] == kbits && kbits > before;
+                if (top) ws.best_sq[owner] = 64u;
+                __syncwarp();
+                if (top) atomicMin(&ws.best_sq[owner], sq);
+                __syncwarp();
+            }
+        }
+        if (!done) {
+            int move = OTHELLO_PASS;
+            u64 f = 0, x = 0;
+            if (moving) {
+                if (evaluate) move = (int)ws.best_sq[lane];
+                else if (random_now) move = kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
+                else move = __ffsll((long long)legal) - 1;
+                x = 1ull << move;
+                f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
+            }
+            if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
+            const u64 moved = own | f | x;                    // put_s (board.py:203-208)
+            own = opp & ~f;
+            opp = moved;
+            black_moves = !black_moves;
+            t++;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int ob_launch_greedy(const othello_playout_args &a, cudaStream_t s)
+{
+    const unsigned blocks = ob_blocks(a.n_games, kThreads);
+    const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;
+    if (a.traj_black) {
+        if (subst) greedy_kernel<true, true><<<blocks, kThreads, 0, s>>>(a);
+        else greedy_kernel<false, true><<<blocks, kThreads, 0, s>>>(a);
+    } else {
+        if (subst) greedy_kernel<true, false><<<blocks, kThreads, 0, s>>>(a);
+        else greedy_kernel<false, false><<<blocks, kThreads, 0, s>>>(a);
+    }
+    return ob_launch_status();
+}

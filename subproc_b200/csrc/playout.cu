@@ -12,66 +12,18 @@
 // which may substitute a uniformly random move for the engine's, an engine with no move answers
 // 'ps' and the pass is a ply of its own (board.py:194-195,203-208); the game stops when neither
 // colour can move (board.py:57-58).
-#include "common.cuh"
-#include "fastboard.cuh"
+#include "playout_common.cuh"
 
 using namespace ob;
+using namespace obp;
 
 namespace {
 
-constexpr int kThreads = 128;
-
-struct Choice { int move; u64 flips; };
-
-// ray masks for obf::flips_for, [direction][square] so that lanes with different squares spread
-// over the shared-memory banks (2 KB per CTA)
-struct Rays {
-    const u64 *t;
-    __device__ __forceinline__ u64 operator()(int d, int s) const { return t[d * 64 + s]; }
-};
-
-__device__ __forceinline__ void fill_rays(u64 *t)
-{
-    for (int i = threadIdx.x; i < obf::kRayDirs * 64; i += blockDim.x) t[i] = obf::make_ray(i >> 6, i & 63);
-}
-
-// w[phase] . (mobility, a..h) + w[phase][9] with the tuned move generator
-__device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__restrict__ w)
-{
-    const int discs = __popcll(own | opp);
-    const float *row = w + 10 * phase_row(discs);
-    float acc = row[9];
-    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)__popcll(own & kClassMask[k]), acc);
-    return acc;
-}
-
-// the greedy engine: arg-max over puttables() (ascending square) of the linear evaluation of
-// the successor from the mover's side; strict '>' keeps the lowest square on ties
-__device__ __forceinline__ Choice greedy_choice(u64 legal, u64 own, u64 opp, u64 own_r, u64 opp_r, const Rays &rays,
-                                                const float *w_s)
-{
-    Choice best = {-1, 0ull};
-    float best_v = 0.f;
-    for (u64 rem = legal; rem; rem &= rem - 1) {
-        const int s = __ffsll((long long)rem) - 1;
-        const u64 x = 1ull << s;
-        const u64 f = obf::flips_for(s, own, opp, own_r, opp_r, rays);
-        const float v = eval_fast(own | f | x, opp & ~f, w_s);
-        if (best.move < 0 || v > best_v) { best.move = s; best.flips = f; best_v = v; }
-    }
-    return best;
-}
-
-template <bool GREEDY, bool SUBST, bool TRAJ>
+// the random engine (uniform over puttables()); the greedy engine lives in greedy.cu
+template <bool TRAJ>
 __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout_args a)
 {
-    __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
     __shared__ u64 ray_s[obf::kRayDirs * 64];
-    if (GREEDY) {
-        if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = a.weights[threadIdx.x];
-    }
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
@@ -84,8 +36,6 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
     u64 own = black_moves ? b0 : w0, opp = black_moves ? w0 : b0;
 
     const u32 key = rng_key(a.seed, a.gid0 + (u64)g);
-    // n_rand_rest = min(n_rand_hands, N_RAND_HAND_UNTIL = 10) (game_runner.py:6,118-119)
-    int rest_b = SUBST ? min(a.n_rand_black, 10) : 0, rest_w = SUBST ? min(a.n_rand_white, 10) : 0;
 
     u64 *tb = TRAJ ? (u64 *)a.traj_black + g : nullptr;
     u64 *tw = TRAJ ? (u64 *)a.traj_white + g : nullptr;
@@ -109,22 +59,12 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
         } else {
             const int n = __popcll(legal);
             const u32 r1 = rng_draw(key, (u32)t, 1u);
-            bool random_now = !GREEDY || t < a.random_plies;
-            if (SUBST) {
-                const int rest = black_moves ? rest_b : rest_w;
-                if (rest > 0 && rng_below(rng_draw(key, (u32)t, 0u), (u32)rest) == 0) {   // game_runner.py:134-135
-                    random_now = true;
-                    if (black_moves) rest_b--; else rest_w--;
-                }
-            }
-            if (GREEDY && !random_now) {
-                const Choice c = greedy_choice(legal, own, opp, own_r, opp_r, rays, w_s);
-                move = c.move; f = c.flips; x = 1ull << move;
-            } else {
-                move = kth_set_bit(legal, (int)rng_below(r1, (u32)n));
-                x = 1ull << move;
-                f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
-            }
+            // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
+            // random one; behind a random engine both draw the same k-th move from stream 1, so the
+            // budgets n_rand_* do not change any game played by this kernel.
+            move = kth_set_bit(legal, (int)rng_below(r1, (u32)n));
+            x = 1ull << move;
+            f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
         }
         if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
         // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
@@ -139,12 +79,11 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
     a.final_white[g] = black_moves ? opp : own;
 }
 
-template <bool GREEDY, bool SUBST>
 int launch(const othello_playout_args &a, cudaStream_t s)
 {
     const unsigned blocks = ob_blocks(a.n_games, kThreads);
-    if (a.traj_black) playout_kernel<GREEDY, SUBST, true><<<blocks, kThreads, 0, s>>>(a);
-    else playout_kernel<GREEDY, SUBST, false><<<blocks, kThreads, 0, s>>>(a);
+    if (a.traj_black) playout_kernel<true><<<blocks, kThreads, 0, s>>>(a);
+    else playout_kernel<false><<<blocks, kThreads, 0, s>>>(a);
     return ob_launch_status();
 }
 
@@ -164,8 +103,7 @@ extern "C" int othello_playout(const othello_playout_args *args, void *stream)
     if (a.traj_black || a.traj_white || a.traj_move)
         OB_CHECK_ARGS(a.traj_black && a.traj_white && a.traj_move && a.t_max >= 0 && a.stride >= a.n_games);
     const bool greedy = a.policy == OTHELLO_POLICY_GREEDY;
-    const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (greedy) return subst ? launch<true, true>(a, s) : launch<true, false>(a, s);
-    return subst ? launch<false, true>(a, s) : launch<false, false>(a, s);
+    if (greedy) return ob_launch_greedy(a, s);
+    return launch(a, s);
 }

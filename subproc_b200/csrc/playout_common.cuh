@@ -1,0 +1,47 @@
+// playout_common.cuh -- pieces shared by the random (playout.cu) and greedy (greedy.cu) game kernels
+#pragma once
+#include "common.cuh"
+#include "fastboard.cuh"
+
+namespace obp {
+
+using ob::u64;
+using ob::u32;
+
+constexpr int kThreads = 128;
+
+// ray masks for obf::flips_for, [direction][square] so that lanes with different squares spread
+// over the shared-memory banks (2 KB per CTA)
+struct Rays {
+    const u64 *t;
+    __device__ __forceinline__ u64 operator()(int d, int s) const { return t[d * 64 + s]; }
+};
+
+__device__ __forceinline__ void fill_rays(u64 *t)
+{
+    for (int i = threadIdx.x; i < obf::kRayDirs * 64; i += blockDim.x) t[i] = obf::make_ray(i >> 6, i & 63);
+}
+
+// w[phase] . (mobility, a..h) + w[phase][9] with the tuned move generator
+__device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__restrict__ w)
+{
+    const int discs = __popcll(own | opp);
+    const float *row = w + 10 * ob::phase_row(discs);
+    float acc = row[9];
+    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)__popcll(own & ob::kClassMask[k]), acc);
+    return acc;
+}
+
+// go_for's substitution test (game_runner.py:134-135): with budget `rest` left, play a random move
+// with probability 1/rest (stream 0 of the counter-based RNG)
+__device__ __forceinline__ bool substitute_now(u32 key, int t, int rest)
+{
+    return rest > 0 && ob::rng_below(ob::rng_draw(key, (u32)t, 0u), (u32)rest) == 0;
+}
+
+}  // namespace obp
+
+// greedy.cu
+int ob_launch_greedy(const othello_playout_args &a, cudaStream_t s);
