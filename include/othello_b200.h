@@ -83,6 +83,12 @@ int othello_counts(const uint64_t *black, const uint64_t *white, int32_t *out, i
 int othello_mask_count(const uint64_t *black, const uint64_t *white, const uint8_t *color, const uint64_t *mask,
                        int32_t *out, int64_t n, void *stream);
 
+/* Board.serialize_board / Board.deserialize (board.py:223-262): the 64-character row-major board
+ * string of the recorder schema ('O' = Black, 'X' = White, '-' = empty; game_recorder.py:108-113).
+ * chars: DEVICE char[n][64], 8-byte aligned.  Any other character deserialises to an empty square. */
+int othello_serialize_boards(const uint64_t *black, const uint64_t *white, char *chars, int64_t n, void *stream);
+int othello_deserialize_boards(const char *chars, uint64_t *black, uint64_t *white, int64_t n, void *stream);
+
 /* ---- features and evaluation ---------------------------------------------------------------- */
 
 /* counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17): out[n][10] =
@@ -146,6 +152,28 @@ int othello_learn_accumulate(const uint64_t *traj_black, const uint64_t *traj_wh
                              const uint64_t *final_black, const uint64_t *final_white,
                              int64_t n_games, int64_t stride, int32_t t_max, const double *decay /* [t_max+1] */,
                              double *stats, void *stream);
+
+/* ---- the reference's value table, exactly ------------------------------------------------------ */
+
+/* __update_state_for_a_book (progress_position_moves_learn.py:37-48): one (key, new_value) record per
+ * (position, side) written AT ITS PLACE IN THE REFERENCE'S UPDATE ORDER -- games ascending, positions
+ * terminal -> start (replearn.py:37-38), 'O' then 'X' (:44-47).  Game g's records start at rec_base[g]
+ * (exclusive prefix sum of 2 * (nplies + 1), computed by the caller).  key = counts() packed into 43
+ * bits: discs(7) mobility(6) a(3) b(4) c(3) d(4) e(4) f(5) g(3) h(4), most significant first. */
+int othello_value_records(const uint64_t *traj_black, const uint64_t *traj_white, const int32_t *nplies,
+                          const uint64_t *final_black, const uint64_t *final_white, int64_t n_games, int64_t stride,
+                          int32_t t_max, const double *decay /* [t_max+1] */, const int64_t *rec_base,
+                          uint64_t *keys, double *targets, void *stream);
+
+/* __update_state_map (:50-62) for runs of records that share a key: segment s covers
+ * targets[seg_start[s] .. seg_start[s+1]) in update order and starts from init[s] (0 = key not in the
+ * table); V = new if V == 0 else V*(1-a) + new*a, evaluated sequentially in fp64 with the reference's
+ * rounding (no fused multiply-add).  out[s] = the value the table holds afterwards. */
+int othello_value_smooth(const double *targets, const int64_t *seg_start, const double *init, double a, double *out,
+                         int64_t n_seg, void *stream);
+
+/* packed key -> the 10 integers of counts() (features[n][10]) */
+int othello_unpack_keys(const uint64_t *keys, int32_t *features, int64_t n, void *stream);
 
 /* ---- measurement helper --------------------------------------------------------------------- */
 

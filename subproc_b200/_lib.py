@@ -43,6 +43,8 @@ SIGNATURES = {
     "othello_step": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "othello_counts": (ctypes.c_int, [vp, vp, vp, i64, vp]),
     "othello_mask_count": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
+    "othello_serialize_boards": (ctypes.c_int, [vp, vp, vp, i64, vp]),
+    "othello_deserialize_boards": (ctypes.c_int, [vp, vp, vp, i64, vp]),
     "othello_features": (ctypes.c_int, [vp, vp, vp, vp, i64, vp]),
     "othello_eval": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
     "othello_playout": (ctypes.c_int, [ctypes.POINTER(PlayoutArgs), vp]),
@@ -50,6 +52,9 @@ SIGNATURES = {
     "othello_perft": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, i64,
                                      u64p, vp]),
     "othello_learn_accumulate": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp]),
+    "othello_value_records": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
+    "othello_value_smooth": (ctypes.c_int, [vp, vp, vp, ctypes.c_double, vp, i64, vp]),
+    "othello_unpack_keys": (ctypes.c_int, [vp, vp, i64, vp]),
     "othello_int32_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "othello_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
     "othello_ctx_destroy": (None, [vp]),

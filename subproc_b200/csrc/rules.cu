@@ -135,9 +135,69 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const u64 *__restrict__ 
     out[i] = eval_linear(is_black ? b : w, is_black ? w : b, w_s);
 }
 
+// Board.serialize_board (board.py:223-243): 64 characters per position, row-major, 'O' = Black,
+// 'X' = White, '-' = empty.  One thread writes one rank (8 characters = one 8-byte store), so a warp
+// writes 256 contiguous bytes: an HBM-bound codec (16 B read, 64 B written per position).
+__global__ void __launch_bounds__(kThreads) serialize_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
+                                                             u64 *__restrict__ out /* [n][8] */, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n * 8) return;
+    const int64_t pos = i >> 3;
+    const int rank = (int)(i & 7);
+    const unsigned b = (unsigned)(black[pos] >> (8 * rank)) & 0xFFu, w = (unsigned)(white[pos] >> (8 * rank)) & 0xFFu;
+    u64 chars = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        const unsigned c = ((b >> x) & 1u) ? 'O' : (((w >> x) & 1u) ? 'X' : '-');
+        chars |= (u64)c << (8 * x);
+    }
+    out[i] = chars;
+}
+
+// Board.deserialize (board.py:253-262) of the 64-character board string; any character other than
+// 'O' / 'X' is an empty square (turn_from_string, board.py:245-251).  One thread per position reads
+// its 64 bytes as eight 8-byte words.
+__global__ void __launch_bounds__(kThreads) deserialize_kernel(const u64 *__restrict__ in /* [n][8] */,
+                                                               u64 *__restrict__ black, u64 *__restrict__ white, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    u64 b = 0, w = 0;
+#pragma unroll
+    for (int rank = 0; rank < 8; rank++) {
+        const u64 chars = in[i * 8 + rank];
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const unsigned c = (unsigned)(chars >> (8 * x)) & 0xFFu;
+            if (c == 'O') b |= 1ull << (8 * rank + x);
+            else if (c == 'X') w |= 1ull << (8 * rank + x);
+        }
+    }
+    black[i] = b; white[i] = w;
+}
+
 }  // namespace
 
 extern "C" {
+
+int othello_serialize_boards(const uint64_t *black, const uint64_t *white, char *out, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && out)) && ((uintptr_t)out & 7) == 0);
+    if (n == 0) return 0;
+    serialize_kernel<<<ob_blocks(n * 8, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black,
+                                                                                      (const u64 *)white, (u64 *)out, n);
+    return ob_launch_status();
+}
+
+int othello_deserialize_boards(const char *in, uint64_t *black, uint64_t *white, int64_t n, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && in)) && ((uintptr_t)in & 7) == 0);
+    if (n == 0) return 0;
+    deserialize_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)in, (u64 *)black,
+                                                                                    (u64 *)white, n);
+    return ob_launch_status();
+}
 
 int othello_legal(const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n, void *stream)
 {

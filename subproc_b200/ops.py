@@ -129,6 +129,29 @@ def mask_count(black, white, color, mask):
     return out
 
 
+def serialize_boards(black, white):
+    """uint8 [n][64]: Board.serialize_board() of every position (board.py:223-243)."""
+    n = black.numel()
+    out = torch.empty((n, 64), dtype=torch.uint8, device=black.device)
+    with torch.cuda.device(black.device):
+        _lib.check(_lib.lib().othello_serialize_boards(
+            _req(black, torch.int64, n, "black"), _req(white, torch.int64, n, "white"),
+            _req(out, torch.uint8, 64 * n, "out"), n, _stream(black)), "othello_serialize_boards")
+    return out
+
+
+def deserialize_boards(chars):
+    """uint8 [n][64] board strings -> (black, white) int64 [n] (Board.deserialize, board.py:253-262)."""
+    n = chars.shape[0]
+    black = torch.empty(n, dtype=torch.int64, device=chars.device)
+    white = torch.empty(n, dtype=torch.int64, device=chars.device)
+    with torch.cuda.device(chars.device):
+        _lib.check(_lib.lib().othello_deserialize_boards(
+            _req(chars, torch.uint8, 64 * n, "chars"), _req(black, torch.int64, n, "black"),
+            _req(white, torch.int64, n, "white"), n, _stream(chars)), "othello_deserialize_boards")
+    return black, white
+
+
 def features(black, white, side):
     """[n][10] int32 = counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17)."""
     n = black.numel()
