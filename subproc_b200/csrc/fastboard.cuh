@@ -125,21 +125,80 @@ OBF_HD u64 ray_flips(u64 x, u64 R, u64 own, u64 opp)
     return closed ? run : 0ull;
 }
 
+#if defined(__CUDACC__)
+// An integer 1 the compiler cannot see through: multiplying by it keeps an addition on the FMA pipe
+// (IMAD) instead of the saturated ALU pipe (IADD3 / SEL / LOP3).
+static __device__ __constant__ u32 kOpaqueOne = 1u;
+
+// acc += run when the ray is closed.  The flipped runs of the 8 rays are pairwise disjoint, so the
+// OR-accumulation of put() is an ADD; gated by a predicate and issued as IMAD it costs the ALU pipe
+// two instructions (OR of the two halves of `closed`, compare) instead of five.
+__device__ __forceinline__ void ray_accumulate(u32 &acc_lo, u32 &acc_hi, u64 x, u64 R, u64 own, u64 opp, u32 one)
+{
+    const u64 sum = (opp | ~R) + x;
+    const u64 closed = sum & own & R;
+    const u64 run = R & opp & ~sum;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p mad.lo.u32 %0, %2, %5, %0;\n\t@p mad.lo.u32 %1, %3, %5, %1;\n\t}"
+        : "+r"(acc_lo), "+r"(acc_hi)
+        : "r"(lo32(run)), "r"(hi32(run)), "r"(lo32(closed) | hi32(closed)), "r"(one));
+}
+#endif
+
+#if defined(__CUDACC__)
+// index of the k-th (0-based, ascending) set bit of a non-empty mask, k < popc(mask): puttables()[k]
+// (board.py:48-51).  Binary search on POPC (XU pipe); the conditional updates of k and of the bit
+// base are predicated IMADs (FMA pipe), so a step costs the ALU pipe three instructions.
+__device__ __forceinline__ int kth_set_bit(u64 mask, int k)
+{
+    const u32 one = kOpaqueOne;
+    u32 v = lo32(mask);
+    int base = 0;
+    {
+        const int c = __popc(v);
+        const u32 hi = hi32(mask);
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, %3;\n\t@p mov.b32 %0, %4;\n\t@p mad.lo.s32 %2, %5, 32, %2;\n\t"
+            "@p mad.lo.s32 %1, %3, %6, %1;\n\t}"
+            : "+r"(v), "+r"(k), "+r"(base) : "r"(c), "r"(hi), "r"(one), "r"(0u - one));
+    }
+#define OBF_KTH_STEP(W, M)                                                                                         \
+    {                                                                                                              \
+        const int c = __popc(v & (M));                                                                             \
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, %3;\n\t@p shr.u32 %0, %0, " #W ";\n\t"                        \
+            "@p mad.lo.s32 %2, %4, " #W ", %2;\n\t@p mad.lo.s32 %1, %3, %5, %1;\n\t}"                                \
+            : "+r"(v), "+r"(k), "+r"(base) : "r"(c), "r"(one), "r"(0u - one));                                     \
+    }
+    OBF_KTH_STEP(16, 0xFFFFu)
+    OBF_KTH_STEP(8, 0xFFu)
+    OBF_KTH_STEP(4, 0xFu)
+    OBF_KTH_STEP(2, 0x3u)
+#undef OBF_KTH_STEP
+    return base + ((k >= (int)(v & 1u)) ? 1 : 0);
+}
+#endif
+
 // Discs flipped by an `own` disc on the EMPTY square s (board.py:161-174); rays = table [4][64].
 template <typename RayTable>
 OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTable &rays)
 {
     const int sr = 63 - s;
     const u64 x = 1ull << s, xr = 1ull << sr;
-    u64 f = 0, fr = 0;
 #if defined(__CUDA_ARCH__)
+    const u32 one = kOpaqueOne;
+    u32 f_lo = 0, f_hi = 0, r_lo = 0, r_hi = 0;
 #pragma unroll
-#endif
+    for (int d = 0; d < kRayDirs; d++) {
+        ray_accumulate(f_lo, f_hi, x, rays(d, s), own, opp, one);
+        ray_accumulate(r_lo, r_hi, xr, rays(d, sr), own_r, opp_r, one);
+    }
+    return pack(f_lo, f_hi) | rev64(pack(r_lo, r_hi));
+#else
+    u64 f = 0, fr = 0;
     for (int d = 0; d < kRayDirs; d++) {
         f |= ray_flips(x, rays(d, s), own, opp);
         fr |= ray_flips(xr, rays(d, sr), own_r, opp_r);
     }
     return f | rev64(fr);
+#endif
 }
 
 }  // namespace obf

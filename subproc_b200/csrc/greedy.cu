@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_
             u64 f = 0, x = 0;
             if (moving) {
                 if (evaluate) move = (int)ws.best_sq[lane];
-                else if (random_now) move = kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
+                else if (random_now) move = obf::kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
                 else move = __ffsll((long long)legal) - 1;
                 x = 1ull << move;
                 f = obf::flips_for(move, own, opp, own_r, opp_r, rays);

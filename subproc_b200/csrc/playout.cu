@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) playout_kernel(const othello_playout
             // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
             // random one; behind a random engine both draw the same k-th move from stream 1, so the
             // budgets n_rand_* do not change any game played by this kernel.
-            move = kth_set_bit(legal, (int)rng_below(r1, (u32)n));
+            move = obf::kth_set_bit(legal, (int)rng_below(r1, (u32)n));
             x = 1ull << move;
             f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
         }
