@@ -10,9 +10,10 @@
 // to the normal equations of its disc-count shard (:112-113).  The 4 x 112 doubles are the only
 // thing ranks exchange (one NCCL all-reduce); the 10x10 solves are done by the host.
 //
-// Reads 16 B per position (coalesced rows of the SoA trajectory) and ~1.5 k integer
-// instructions per position; XtX is accumulated in integers (exact), Xty / sum y^2 in fp64.
+// Reads 16 B per position (coalesced rows of the SoA trajectory); XtX is accumulated in integers
+// (exact), Xty / sum y^2 in fp64.
 #include "common.cuh"
+#include "fastboard.cuh"
 
 using namespace ob;
 
@@ -21,6 +22,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kX = 10;                       // regressors incl. intercept
 constexpr int kPairs = kX * (kX + 1) / 2;    // upper triangle of XtX
+constexpr int kF = kX + 2;                   // Xty[10], n, sum y^2
 constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ constexpr int pair_index(int i, int j) { return i * kX - i * (i - 1) / 2 + (j - i); }
@@ -32,6 +34,38 @@ __device__ __forceinline__ double warp_sum_f64(double v)
     return v;
 }
 
+// Every lane keeps the statistics of the shard it is currently seeing in REGISTERS (55 integer
+// products on the FMA pipe + 12 fp64 sums per position) and spills them to the CTA's shared-memory
+// totals only when its shard changes -- tiles are walked in ply order, so that is ~4 times per lane --
+// and once at the end through warp reductions.
+struct LaneAcc {
+    unsigned xtx[kPairs];
+    double f[kF];
+    int shard;
+};
+
+__device__ __forceinline__ void lane_clear(LaneAcc &a, int shard)
+{
+#pragma unroll
+    for (int p = 0; p < kPairs; p++) a.xtx[p] = 0u;
+#pragma unroll
+    for (int k = 0; k < kF; k++) a.f[k] = 0.0;
+    a.shard = shard;
+}
+
+// a single lane hands its partial sums to the CTA totals (rare: shard change inside a lane)
+__device__ __forceinline__ void lane_spill(LaneAcc &a, unsigned long long (*s_xtx)[kPairs], double (*s_f)[kF])
+{
+    if (a.shard >= 0) {
+#pragma unroll
+        for (int p = 0; p < kPairs; p++)
+            if (a.xtx[p]) atomicAdd(&s_xtx[a.shard][p], (unsigned long long)a.xtx[p]);
+#pragma unroll
+        for (int k = 0; k < kF; k++)
+            if (a.f[k] != 0.0) atomicAdd(&s_f[a.shard][k], a.f[k]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__ traj_black,
                                                          const u64 *__restrict__ traj_white,
                                                          const int32_t *__restrict__ nplies,
@@ -41,66 +75,66 @@ __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__
                                                          double *__restrict__ stats)
 {
     __shared__ unsigned long long s_xtx[OTHELLO_PHASES][kPairs];
-    __shared__ double s_f[OTHELLO_PHASES][kX + 2];          // Xty[10], n, sum y^2
+    __shared__ double s_f[OTHELLO_PHASES][kF];
     for (int i = threadIdx.x; i < OTHELLO_PHASES * kPairs; i += kThreads) (&s_xtx[0][0])[i] = 0ull;
-    for (int i = threadIdx.x; i < OTHELLO_PHASES * (kX + 2); i += kThreads) (&s_f[0][0])[i] = 0.0;
+    for (int i = threadIdx.x; i < OTHELLO_PHASES * kF; i += kThreads) (&s_f[0][0])[i] = 0.0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int64_t tiles_per_row = (n_games + kThreads - 1) / kThreads;
     const int64_t tiles = tiles_per_row * (int64_t)(t_max + 1);
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // contiguous, ply-major ranges of tiles per CTA: the shard changes a handful of times per lane
+    const int64_t first = tiles * blockIdx.x / gridDim.x, last = tiles * (blockIdx.x + 1) / gridDim.x;
+    LaneAcc acc;
+    lane_clear(acc, -1);
+    for (int64_t tile = first; tile < last; tile++) {
         const int t = (int)(tile / tiles_per_row);
         const int64_t g = (tile % tiles_per_row) * kThreads + threadIdx.x;
         int len = -1;
         if (g < n_games) len = nplies[g];
-        const bool valid = t <= len && len <= t_max;          // positions 0..nplies are recorded; truncated games are skipped
-        if (!__any_sync(kFull, valid)) continue;
-
+        if (t > len || len > t_max) continue;                 // positions 0..nplies are recorded; truncated games are skipped
+        const u64 b = traj_black[(int64_t)t * stride + g], w = traj_white[(int64_t)t * stride + g];
+        const int shard = phase_row(__popcll(b | w));
+        if (shard != acc.shard) { lane_spill(acc, s_xtx, s_f); lane_clear(acc, shard); }
         int xb[kX], xw[kX];
-        double y = 0.0;
-        int shard = -1;
+        const u64 br = obf::rev64(b), wr = obf::rev64(w);
+        xb[0] = __popcll(obf::legal_moves(b, w, br, wr));
+        xw[0] = __popcll(obf::legal_moves(w, b, wr, br));
 #pragma unroll
-        for (int k = 0; k < kX; k++) xb[k] = xw[k] = 0;
-        if (valid) {
-            const u64 b = traj_black[(int64_t)t * stride + g], w = traj_white[(int64_t)t * stride + g];
-            shard = phase_row(__popcll(b | w));
-            xb[0] = __popcll(legal_moves(b, w));
-            xw[0] = __popcll(legal_moves(w, b));
+        for (int k = 0; k < 8; k++) {
+            xb[1 + k] = __popcll(b & kClassMask[k]);
+            xw[1 + k] = __popcll(w & kClassMask[k]);
+        }
+        xb[9] = xw[9] = 1;
+        const int value = __popcll(final_black[g]) - __popcll(final_white[g]);       // value_for_black (:40-42)
+        const double y = (double)value * decay[len - t];                             // * l ** turn_left (:55)
+        // XtX: both sides at once, exact integer sums
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                xb[1 + k] = __popcll(b & kClassMask[k]);
-                xw[1 + k] = __popcll(w & kClassMask[k]);
-            }
-            xb[9] = xw[9] = 1;
-            const int value = __popcll(final_black[g]) - __popcll(final_white[g]);   // value_for_black (:40-42)
-            y = (double)value * decay[len - t];                                     // * l ** turn_left (:55)
+        for (int i = 0; i < kX; i++) {
+#pragma unroll
+            for (int j = i; j < kX; j++) acc.xtx[pair_index(i, j)] += (unsigned)(xb[i] * xb[j] + xw[i] * xw[j]);
+        }
+        // Xty: White's target is the negative of Black's (value_for_white, :42)
+#pragma unroll
+        for (int i = 0; i < kX; i++) acc.f[i] += (double)(xb[i] - xw[i]) * y;
+        acc.f[kX] += 2.0;
+        acc.f[kX + 1] += 2.0 * y * y;
+    }
+    // end of the CTA's range: reduce over the warp per shard, one atomic per value per warp
+#pragma unroll 1
+    for (int s = 0; s < OTHELLO_PHASES; s++) {
+        const bool in = acc.shard == s;
+        if (!__any_sync(kFull, in)) continue;
+#pragma unroll
+        for (int p = 0; p < kPairs; p++) {
+            // 32 lanes x (tiles per CTA) x 2 * 64 * 64 stays far below 2^32
+            const unsigned r = __reduce_add_sync(kFull, in ? acc.xtx[p] : 0u);
+            if (lane == (p & 31) && r) atomicAdd(&s_xtx[s][p], (unsigned long long)r);
         }
 #pragma unroll
-        for (int s = 0; s < OTHELLO_PHASES; s++) {
-            const bool in = shard == s;
-            if (!__any_sync(kFull, in)) continue;
-            // XtX: both sides at once, exact integer sums
-#pragma unroll
-            for (int i = 0; i < kX; i++) {
-#pragma unroll
-                for (int j = i; j < kX; j++) {
-                    const int p = in ? xb[i] * xb[j] + xw[i] * xw[j] : 0;
-                    const int r = __reduce_add_sync(kFull, p);
-                    if (lane == (pair_index(i, j) & 31)) atomicAdd(&s_xtx[s][pair_index(i, j)], (unsigned long long)r);
-                }
-            }
-            // Xty: White's target is the negative of Black's (value_for_white, :42)
-            const double ys = in ? y : 0.0;
-#pragma unroll
-            for (int i = 0; i < kX; i++) {
-                const double r = warp_sum_f64((double)(xb[i] - xw[i]) * ys);
-                if (lane == i) atomicAdd(&s_f[s][i], r);
-            }
-            const double cnt = warp_sum_f64(in ? 2.0 : 0.0);
-            if (lane == 10) atomicAdd(&s_f[s][kX], cnt);
-            const double yy = warp_sum_f64(2.0 * ys * ys);
-            if (lane == 11) atomicAdd(&s_f[s][kX + 1], yy);
+        for (int k = 0; k < kF; k++) {
+            const double r = warp_sum_f64(in ? acc.f[k] : 0.0);
+            if (lane == k && r != 0.0) atomicAdd(&s_f[s][k], r);
         }
     }
     __syncthreads();
