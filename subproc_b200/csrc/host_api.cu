@@ -5,9 +5,13 @@
 #include <new>
 #include "common.cuh"
 
+constexpr int kPipeStreams = 3;     // playout_host pipelines H2D / kernel / D2H of game chunks over these
+
 struct othello_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t pipe[kPipeStreams];
+    cudaEvent_t ready, done[kPipeStreams];
     char *ws;
     size_t ws_bytes;
     // last playout trajectory (views into ws)
@@ -67,6 +71,12 @@ int othello_ctx_create(int device, othello_ctx **out)
     c->traj_black = c->traj_white = nullptr; c->traj_move = nullptr; c->traj_stride = 0; c->traj_t_max = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return (int)e; }
+    e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
+    for (int i = 0; i < kPipeStreams && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { delete c; return (int)e; }
     *out = c;
     return 0;
 }
@@ -76,6 +86,8 @@ void othello_ctx_destroy(othello_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->ws) cudaFree(c->ws);
+    for (int i = 0; i < kPipeStreams; i++) { cudaStreamDestroy(c->pipe[i]); cudaEventDestroy(c->done[i]); }
+    cudaEventDestroy(c->ready);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -153,32 +165,51 @@ int othello_playout_host(othello_ctx *c, uint64_t seed, uint64_t gid0, int64_t n
     uint64_t *d_tb = k.take<uint64_t>((size_t)(t_max + 1) * n), *d_tw = k.take<uint64_t>((size_t)(t_max + 1) * n);
     uint8_t *d_tm = k.take<uint8_t>((size_t)t_max * n + 1);
     cudaStream_t s = c->stream;
-    if (black0) {
-        OB_CUDA(cudaMemcpyAsync(d_b0, black0, n * 8, cudaMemcpyHostToDevice, s));
-        OB_CUDA(cudaMemcpyAsync(d_w0, white0, n * 8, cudaMemcpyHostToDevice, s));
-    }
-    if (turn0) OB_CUDA(cudaMemcpyAsync(d_t0, turn0, n, cudaMemcpyHostToDevice, s));
     if (weights) OB_CUDA(cudaMemcpyAsync(d_wt, weights, sizeof(float) * OTHELLO_PHASES * OTHELLO_WEIGHTS, cudaMemcpyHostToDevice, s));
+    OB_CUDA(cudaEventRecord(c->ready, s));
 
-    othello_playout_args a;
-    a.seed = seed; a.gid0 = gid0; a.n_games = n;
-    a.black0 = black0 ? d_b0 : nullptr; a.white0 = black0 ? d_w0 : nullptr; a.turn0 = turn0 ? d_t0 : nullptr;
-    a.policy = policy; a.random_plies = random_plies; a.n_rand_black = n_rand_black; a.n_rand_white = n_rand_white;
-    a.weights = weights ? d_wt : nullptr;
-    a.t_max = t_max; a.stride = n;
-    a.traj_black = d_tb; a.traj_white = d_tw; a.traj_move = d_tm;
-    a.nplies = d_np; a.final_black = d_fb; a.final_white = d_fw;
-    rc = othello_playout(&a, s);
-    if (rc) return rc;
+    // Games are independent, so the batch is cut into chunks whose copy-in, kernel and copy-out run
+    // on rotating streams: the PCIe traffic of one chunk hides behind the integer work of the others
+    // (with pinned host buffers; pageable buffers simply serialise).
+    int64_t chunk = (n + 7) / 8;
+    if (chunk < 65536) chunk = 65536;
+    chunk = (chunk + 127) & ~(int64_t)127;
+    int used = 0;
+    for (int64_t c0 = 0, i = 0; c0 < n; c0 += chunk, i++) {
+        const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
+        const int si = (int)(i % kPipeStreams);
+        cudaStream_t st = c->pipe[si];
+        if (i < kPipeStreams) { OB_CUDA(cudaStreamWaitEvent(st, c->ready, 0)); used = (int)i + 1; }
+        if (black0) {
+            OB_CUDA(cudaMemcpyAsync(d_b0 + c0, black0 + c0, m * 8, cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaMemcpyAsync(d_w0 + c0, white0 + c0, m * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (turn0) OB_CUDA(cudaMemcpyAsync(d_t0 + c0, turn0 + c0, m, cudaMemcpyHostToDevice, st));
+        othello_playout_args a;
+        a.seed = seed; a.gid0 = gid0 + (uint64_t)c0; a.n_games = m;
+        a.black0 = black0 ? d_b0 + c0 : nullptr; a.white0 = black0 ? d_w0 + c0 : nullptr; a.turn0 = turn0 ? d_t0 + c0 : nullptr;
+        a.policy = policy; a.random_plies = random_plies; a.n_rand_black = n_rand_black; a.n_rand_white = n_rand_white;
+        a.weights = weights ? d_wt : nullptr;
+        a.t_max = t_max; a.stride = n;
+        a.traj_black = d_tb + c0; a.traj_white = d_tw + c0; a.traj_move = d_tm + c0;
+        a.nplies = d_np + c0; a.final_black = d_fb + c0; a.final_white = d_fw + c0;
+        rc = othello_playout(&a, st);
+        if (rc) return rc;
+        OB_CUDA(cudaMemcpyAsync(nplies + c0, d_np + c0, m * 4, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(final_black + c0, d_fb + c0, m * 8, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(final_white + c0, d_fw + c0, m * 8, cudaMemcpyDeviceToHost, st));
+        if (traj_black) {
+            // host and device trajectories are both [t][n]: a chunk is a column block
+            OB_CUDA(cudaMemcpy2DAsync(traj_black + c0, (size_t)n * 8, d_tb + c0, (size_t)n * 8, (size_t)m * 8, t_max + 1, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaMemcpy2DAsync(traj_white + c0, (size_t)n * 8, d_tw + c0, (size_t)n * 8, (size_t)m * 8, t_max + 1, cudaMemcpyDeviceToHost, st));
+            if (t_max > 0)
+                OB_CUDA(cudaMemcpy2DAsync(traj_move + c0, (size_t)n, d_tm + c0, (size_t)n, (size_t)m, t_max, cudaMemcpyDeviceToHost, st));
+        }
+    }
     c->traj_black = d_tb; c->traj_white = d_tw; c->traj_move = d_tm; c->traj_stride = n; c->traj_t_max = t_max;
-
-    OB_CUDA(cudaMemcpyAsync(nplies, d_np, n * 4, cudaMemcpyDeviceToHost, s));
-    OB_CUDA(cudaMemcpyAsync(final_black, d_fb, n * 8, cudaMemcpyDeviceToHost, s));
-    OB_CUDA(cudaMemcpyAsync(final_white, d_fw, n * 8, cudaMemcpyDeviceToHost, s));
-    if (traj_black) {
-        OB_CUDA(cudaMemcpyAsync(traj_black, d_tb, (size_t)(t_max + 1) * n * 8, cudaMemcpyDeviceToHost, s));
-        OB_CUDA(cudaMemcpyAsync(traj_white, d_tw, (size_t)(t_max + 1) * n * 8, cudaMemcpyDeviceToHost, s));
-        OB_CUDA(cudaMemcpyAsync(traj_move, d_tm, (size_t)t_max * n, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < used; i++) {
+        OB_CUDA(cudaEventRecord(c->done[i], c->pipe[i]));
+        OB_CUDA(cudaStreamWaitEvent(s, c->done[i], 0));
     }
     OB_CUDA(cudaStreamSynchronize(s));
     return 0;

@@ -1,0 +1,86 @@
+"""The host-buffer front end of the C ABI (othello_*_host): what a non-torch caller binds
+(INTEGRATION.md).  Plain numpy buffers in, plain numpy buffers out; compared with the oracle and with
+the device-pointer path."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from subproc_b200 import _lib, ops
+from gpu_util import DEV, sample_positions
+
+pytestmark = pytest.mark.gpu
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    L = _lib.lib()
+    c = ctypes.c_void_p()
+    assert L.othello_ctx_create(0, ctypes.byref(c)) == 0
+    yield c
+    L.othello_ctx_destroy(c)
+
+
+def test_legal_and_step_host(ctx, oracle):
+    L = _lib.lib()
+    b, w = sample_positions(oracle, 60, seed=61)
+    n = b.size
+    out = np.zeros(n, np.uint64)
+    assert L.othello_legal_host(ctx, P(b), P(w), P(out), n) == 0
+    assert np.array_equal(out, oracle.puttables(b, w, 1))
+    rng = np.random.RandomState(2)
+    turn = rng.randint(1, 3, size=n).astype(np.uint8)
+    nturn = rng.randint(0, 60, size=n).astype(np.int32)
+    move = rng.randint(0, 66, size=n).astype(np.uint8)
+    wb, ww, wt, wnt, wfl, wret = oracle.step(b, w, turn, nturn, move)
+    hb, hw, ht, hnt = b.copy(), w.copy(), turn.copy(), nturn.copy()
+    fl, ret, flags = np.zeros(n, np.uint64), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    assert L.othello_step_host(ctx, P(hb), P(hw), P(ht), P(hnt), P(move), P(fl), P(ret), P(flags), n) == 0
+    assert np.array_equal(hb, wb) and np.array_equal(hw, ww) and np.array_equal(ht, wt) and np.array_equal(hnt, wnt)
+    assert np.array_equal(fl, wfl) and np.array_equal(ret, wret)
+    assert L.othello_legal_host(ctx, None, None, None, 0) == 0 and L.othello_legal_host(ctx, None, None, None, 3) == -1
+
+
+def test_playout_host_small_with_host_trajectory(ctx, oracle):
+    L = _lib.lib()
+    n, t_max = 777, 70
+    b0, w0 = sample_positions(oracle, 30, seed=62, stride=2)
+    b0, w0 = np.ascontiguousarray(b0[:n]), np.ascontiguousarray(w0[:n])
+    turn0 = (np.arange(n) % 2 + 1).astype(np.uint8)
+    tb, tw = np.zeros((t_max + 1, n), np.uint64), np.zeros((t_max + 1, n), np.uint64)
+    tm = np.zeros((t_max, n), np.uint8)
+    npl, fb, fw = np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    wts = oracle.DEFAULT_WEIGHTS.astype(np.float32)
+    assert L.othello_playout_host(ctx, 7, 1000, n, P(b0), P(w0), P(turn0), 1, 4, 2, 3, P(wts), t_max,
+                                  P(tb), P(tw), P(tm), P(npl), P(fb), P(fw)) == 0
+    ref = oracle.playout(7, 1000, n, black0=b0, white0=w0, turn0=turn0, policy=1, random_plies=4, n_rand_black=2,
+                         n_rand_white=3, t_max=t_max)
+    assert np.array_equal(npl, ref['nplies']) and np.array_equal(fb, ref['final_black']) and np.array_equal(fw, ref['final_white'])
+    t_idx = np.arange(t_max + 1)[:, None]
+    vp = t_idx <= np.minimum(npl, t_max)[None, :]
+    vm = t_idx[:-1] < np.minimum(npl, t_max)[None, :]
+    assert np.array_equal(tb[vp], ref['black'][vp]) and np.array_equal(tw[vp], ref['white'][vp])
+    assert np.array_equal(tm[vm], ref['move'][vm])
+
+
+def test_playout_host_chunked_pipeline_equals_one_launch(ctx):
+    """n large enough for several chunks on rotating streams; results must equal the single-launch path"""
+    L = _lib.lib()
+    n = 300000 + 17
+    npl, fb, fw = np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    assert L.othello_playout_host(ctx, 3, 55, n, None, None, None, 0, 0, 0, 0, None, 120, None, None, None,
+                                  P(npl), P(fb), P(fw)) == 0
+    po = ops.playout(n, seed=3, gid0=55, device=DEV, trajectory=False)
+    assert np.array_equal(npl, po.nplies.cpu().numpy())
+    assert np.array_equal(fb, ops.bits_numpy(po.final_black)) and np.array_equal(fw, ops.bits_numpy(po.final_white))
+    # the trajectory of the last host call stays in device memory owned by the context
+    tbp, twp, tmp = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    stride, tmax = ctypes.c_int64(), ctypes.c_int32()
+    assert L.othello_ctx_trajectory(ctx, ctypes.byref(tbp), ctypes.byref(twp), ctypes.byref(tmp), ctypes.byref(stride),
+                                    ctypes.byref(tmax)) == 0
+    assert stride.value == n and tmax.value == 120 and tbp.value
