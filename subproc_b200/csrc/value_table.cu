@@ -64,6 +64,14 @@ __global__ void __launch_bounds__(kThreads) records_kernel(const u64 *__restrict
     targets[at + 1] = __dmul_rn((double)(-value_black), d);
 }
 
+__device__ __forceinline__ double smooth_step(double v, double nv, double keep, double a)
+{
+    return (v == 0.0) ? nv : __dadd_rn(__dmul_rn(v, keep), __dmul_rn(nv, a));      // :56-61
+}
+
+// One thread per key walks its run in update order.  The recurrence is sequential by definition; the
+// loads are not, so they are issued eight at a time ahead of the dependent fp64 chain (the opening
+// positions are visited by every game: their runs are 2 x n_games long).
 __global__ void __launch_bounds__(kThreads) smooth_kernel(const double *__restrict__ targets,
                                                           const int64_t *__restrict__ seg_start,
                                                           const double *__restrict__ init, double a,
@@ -73,10 +81,16 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const double *__restri
     if (s >= n_seg) return;
     const double keep = __dsub_rn(1.0, a);                                          // (1 - self.a)
     double v = init[s];
-    for (int64_t i = seg_start[s], e = seg_start[s + 1]; i < e; i++) {
-        const double nv = targets[i];
-        v = (v == 0.0) ? nv : __dadd_rn(__dmul_rn(v, keep), __dmul_rn(nv, a));      // :56-61
+    int64_t i = seg_start[s];
+    const int64_t e = seg_start[s + 1];
+    for (; i + 8 <= e; i += 8) {
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = __ldg(targets + i + j);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v = smooth_step(v, x[j], keep, a);
     }
+    for (; i < e; i++) v = smooth_step(v, targets[i], keep, a);
     out[s] = v;
 }
 
