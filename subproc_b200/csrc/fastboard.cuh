@@ -64,20 +64,59 @@ OBF_HD int popc64(u64 v)
 #endif
 }
 
-// Flood to the LEFT (towards higher squares) by D: squares just beyond a run of `m` discs that
-// starts right after an `own` disc.  Kogge-Stone: 1 + 1 + 2 + 2 = up to 6 discs.
-template <int D> OBF_HD u64 flood_up(u64 own, u64 m)
+// ---- move generation in the row-interleaved layout ------------------------------------------------
+// A 64-bit shift that crosses the two 32-bit halves costs an ALU-pipe funnel (SHF.L.U64.HI).  With
+// word a = ranks 1,3,5,7 and word b = ranks 2,4,6,8 (one rank per byte) "one rank down" swaps the
+// words, so every shift of the +8 and +9 floods and half of the +7 ones is a plain 32-bit LEFT shift
+// (IMAD.SHL on the FMA pipe) and "+8" costs one instruction instead of two:
+//     +8: (a, b) -> (b << 8, a)      +16: (a << 8,  b << 8)
+//     +9: (a, b) -> (b << 9, a << 1) +18: (a << 10, b << 10)
+//     +7: (a, b) -> (b << 7, a >> 1) +14: (a << 6,  b << 6)
+// Converting to and from the standard layout is two byte permutes (PRMT) per bitboard; the 180-degree
+// rotation is still two BREVs: rev{a, b} = {brev(b), brev(a)}.
+struct Inter { u32 a, b; };
+
+OBF_HD u32 byte_perm(u32 x, u32 y, u32 sel)
 {
-    u64 f = m & (own << D);
-    f |= m & (f << D);
-    const u64 p = m & (m << D);
-    f |= p & (f << (2 * D));
-    f |= p & (f << (2 * D));
-    return f << D;
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const u64 v = pack(x, y);
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) r |= (u32)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
 }
 
-// Horizontal direction towards higher squares, per 32-bit half (rows never straddle a half and
-// `m` has no a/h-file bits, so no carry and no shifted bit crosses a row): the carry of m + a
+OBF_HD Inter to_inter(u64 v) { return Inter{byte_perm(lo32(v), hi32(v), 0x6420u), byte_perm(lo32(v), hi32(v), 0x7531u)}; }
+OBF_HD u64 from_inter(Inter v) { return pack(byte_perm(v.a, v.b, 0x5140u), byte_perm(v.a, v.b, 0x7362u)); }
+OBF_HD Inter rev_inter(Inter v) { return Inter{brev32(v.b), brev32(v.a)}; }
+OBF_HD Inter iand(Inter x, Inter y) { return Inter{x.a & y.a, x.b & y.b}; }
+OBF_HD Inter ior(Inter x, Inter y) { return Inter{x.a | y.a, x.b | y.b}; }
+
+template <int D> OBF_HD Inter ishift(Inter v)        // D squares up (towards higher squares), D in {7, 8, 9}
+{
+    return D == 8 ? Inter{v.b << 8, v.a} : D == 9 ? Inter{v.b << 9, v.a << 1} : Inter{v.b << 7, v.a >> 1};
+}
+template <int D> OBF_HD Inter ishift2(Inter v)       // 2 * D squares up
+{
+    return D == 8 ? Inter{v.a << 8, v.b << 8} : D == 9 ? Inter{v.a << 10, v.b << 10} : Inter{v.a << 6, v.b << 6};
+}
+
+// Flood to the LEFT (towards higher squares) by D: squares just beyond a run of `m` discs that
+// starts right after an `own` disc.  Kogge-Stone: 1 + 1 + 2 + 2 = up to 6 discs.
+template <int D> OBF_HD Inter flood_up(Inter own, Inter m)
+{
+    Inter f = iand(m, ishift<D>(own));
+    f = ior(f, iand(m, ishift<D>(f)));
+    const Inter p = iand(m, ishift<D>(m));
+    f = ior(f, iand(p, ishift2<D>(f)));
+    f = ior(f, iand(p, ishift2<D>(f)));
+    return ishift<D>(f);
+}
+
+// Horizontal direction towards higher squares, per 32-bit word (a rank never straddles a word and
+// `m` has no a/h-file bits, so no carry and no shifted bit crosses a rank): the carry of m + a
 // ripples through each opponent run that starts right after an own disc and lands behind it.
 OBF_HD u32 row_up32(u32 own, u32 m)
 {
@@ -85,23 +124,27 @@ OBF_HD u32 row_up32(u32 own, u32 m)
     return (m + a) & ~m;                // carry-out squares (bits set by the add that were clear in m)
 }
 
-// the four "up" directions (+1, +7, +8, +9) of one board
-OBF_HD u64 moves_up(u64 own, u64 opp)
+// the four "up" directions (+1, +7, +8, +9) of one board; m = opp without the a/h files
+OBF_HD Inter moves_up(Inter own, Inter opp, Inter m)
 {
-    const u64 m = opp & kInner64;
-    u64 r = pack(row_up32(lo32(own), lo32(m)), row_up32(hi32(own), hi32(m)));
-    r |= flood_up<8>(own, opp);
-    r |= flood_up<7>(own, m);
-    r |= flood_up<9>(own, m);
+    Inter r = Inter{row_up32(own.a, m.a), row_up32(own.b, m.b)};
+    r = ior(r, flood_up<8>(own, opp));
+    r = ior(r, flood_up<7>(own, m));
+    r = ior(r, flood_up<9>(own, m));
     return r;
 }
 
-// Board.puttables(piece) as a mask (board.py:46-52).  own_r / opp_r = rev64(own / opp).
-OBF_HD u64 legal_moves(u64 own, u64 opp, u64 own_r, u64 opp_r)
+// Board.puttables(piece) as a mask (board.py:46-52).
+OBF_HD u64 legal_moves(u64 own, u64 opp)
 {
-    return (moves_up(own, opp) | rev64(moves_up(own_r, opp_r))) & ~(own | opp);
+    const Inter o = to_inter(own), p = to_inter(opp);
+    const Inter m = Inter{p.a & kInner32, p.b & kInner32};
+    const Inter up = moves_up(o, p, m);
+    const Inter down = moves_up(rev_inter(o), rev_inter(p), rev_inter(m));   // the rotated board
+    return from_inter(ior(up, rev_inter(down))) & ~(own | opp);
 }
-OBF_HD u64 legal_moves(u64 own, u64 opp) { return legal_moves(own, opp, rev64(own), rev64(opp)); }
+// (own_r / opp_r = rev64(own / opp) are what flips_for needs; move generation rotates in its own layout)
+OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp); }
 
 // ---- put(): flips through carry propagation along rays -----------------------------------------
 // ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge
