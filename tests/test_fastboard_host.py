@@ -57,3 +57,18 @@ def test_fast_legal_and_flips_match_oracle(fb, oracle):
         fb.fb_flips(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
         _, _, want, _ = oracle.put(b, w, piece, sq)
         assert np.array_equal(out, want)
+
+
+def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
+    """runs of 0..7 opponent discs from every square in every direction, closed / open / into the edge"""
+    import line_cases
+    own, opp, sq = line_cases.build()
+    n = own.size
+    assert n > 5000
+    out = np.zeros(n, dtype=np.uint64)
+    fb.fb_legal(P(own), P(opp), P(out), ctypes.c_long(n))
+    assert np.array_equal(out, oracle.puttables(own, opp, 1))
+    fb.fb_flips(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
+    _, _, want, ret = oracle.put(own, opp, 1, sq)
+    assert np.array_equal(out, want)
+    assert (ret >= 6).sum() > 50 and (ret == 0).sum() > 1000          # six-disc runs and dead rays are both present

@@ -163,3 +163,25 @@ def test_edge_wraparound_lines(oracle):
     sq = rng.randint(0, 64, size=n).astype(np.uint8)
     _, _, want_fl, _ = oracle.put(b, w, 2, sq)
     assert np.array_equal(host_bits(ops.flips(dev_bits(w), dev_bits(b), dev_u8(sq))), want_fl)
+
+
+def test_constructed_lines_every_direction_square_and_run_length(oracle):
+    """both formulations on the GPU (plain Kogge-Stone in rules.cu, tuned in the game kernels) on runs
+    of 0..7 discs from every square in every direction, closed by an own disc / open / into the edge"""
+    import line_cases
+    own, opp, sq = line_cases.build()
+    d_own, d_opp = dev_bits(own), dev_bits(opp)
+    assert np.array_equal(host_bits(ops.legal(d_own, d_opp)), oracle.puttables(own, opp, 1))
+    _, _, want, ret = oracle.put(own, opp, 1, sq)
+    assert np.array_equal(host_bits(ops.flips(d_own, d_opp, dev_u8(sq))), want)
+    # the tuned primitives, through a one-ply greedy search from each position: the chosen move's
+    # successor must equal the oracle's greedy successor
+    n = own.size
+    w = torch.from_numpy(oracle.DEFAULT_WEIGHTS.astype(np.float32)).to(DEV)
+    has_move = oracle.puttables(own, opp, 1) != 0
+    idx = np.nonzero(has_move)[0][:4000]
+    po = ops.playout(idx.size, seed=1, gid0=0, device=DEV, black0=dev_bits(own[idx]), white0=dev_bits(opp[idx]),
+                     policy=ops.POLICY_GREEDY, weights=w, t_max=2)
+    ref = oracle.playout(1, 0, idx.size, black0=own[idx], white0=opp[idx], policy=1, t_max=2)
+    assert np.array_equal(host_bits(po.black[1]), ref['black'][1]) and np.array_equal(host_bits(po.white[1]), ref['white'][1])
+    assert np.array_equal(po.move[0].cpu().numpy(), ref['move'][0])
