@@ -35,6 +35,10 @@ __global__ void __launch_bounds__(kThreads) expand_kernel(const u64 *__restrict_
                                                           int64_t n_in, u64 *__restrict__ out_own,
                                                           u64 *__restrict__ out_opp, int64_t cap, Ctl *ctl)
 {
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     u64 own = 0, opp = 0, legal = 0;
@@ -43,9 +47,9 @@ __global__ void __launch_bounds__(kThreads) expand_kernel(const u64 *__restrict_
     bool pass = false;
     if (i < n_in) {
         own = in_own[i]; opp = in_opp[i];
-        legal = legal_moves(own, opp);
+        legal = obf::legal_moves(own, opp);
         if (legal) cnt = __popcll(legal);
-        else if (legal_moves(opp, own)) { pass = true; cnt = 1; }
+        else if (obf::legal_moves(opp, own)) { pass = true; cnt = 1; }
         else leaf = 1;                                       // game over: one leaf
     }
     // warp-exclusive prefix of cnt, one atomic per warp
@@ -65,33 +69,37 @@ __global__ void __launch_bounds__(kThreads) expand_kernel(const u64 *__restrict_
     int64_t o = (int64_t)base + incl - cnt;
     if (o + cnt > cap) { ctl->overflow = 1; return; }
     if (pass) { out_own[o] = opp; out_opp[o] = own; return; }
+    const u64 own_r = obf::rev64(own), opp_r = obf::rev64(opp);
     for (u64 rem = legal; rem; rem &= rem - 1, o++) {
-        const u64 x = rem & (0 - rem);
-        const u64 f = flips_for(x, own, opp);
+        const int sq = __ffsll((long long)rem) - 1;
+        const u64 x = 1ull << sq;
+        const u64 f = obf::flips_for(sq, own, opp, own_r, opp_r, rays);
         out_own[o] = opp & ~f;                               // the child is seen by its own mover
         out_opp[o] = own | f | x;
     }
 }
 
 template <int R> struct Dfs {
-    static __device__ unsigned long long run(u64 own, u64 opp)
+    static __device__ unsigned long long run(u64 own, u64 opp, const Rays &rays)
     {
-        const u64 legal = legal_moves(own, opp);
-        if (!legal) return legal_moves(opp, own) ? Dfs<R - 1>::run(opp, own) : 1ull;
+        const u64 legal = obf::legal_moves(own, opp);
+        if (!legal) return obf::legal_moves(opp, own) ? Dfs<R - 1>::run(opp, own, rays) : 1ull;
         unsigned long long total = 0;
+        const u64 own_r = obf::rev64(own), opp_r = obf::rev64(opp);
         for (u64 rem = legal; rem; rem &= rem - 1) {
-            const u64 x = rem & (0 - rem);
-            const u64 f = flips_for(x, own, opp);
-            total += Dfs<R - 1>::run(opp & ~f, own | f | x);
+            const int sq = __ffsll((long long)rem) - 1;
+            const u64 x = 1ull << sq;
+            const u64 f = obf::flips_for(sq, own, opp, own_r, opp_r, rays);
+            total += Dfs<R - 1>::run(opp & ~f, own | f | x, rays);
         }
         return total;
     }
 };
 template <> struct Dfs<1> {
     // one ply left: every move, or the pass, or the game-over node itself, is exactly one leaf
-    static __device__ unsigned long long run(u64 own, u64 opp)
+    static __device__ unsigned long long run(u64 own, u64 opp, const Rays &)
     {
-        const u64 legal = legal_moves(own, opp);
+        const u64 legal = obf::legal_moves(own, opp);
         return legal ? (unsigned long long)__popcll(legal) : 1ull;
     }
 };
@@ -100,9 +108,13 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) dfs_kernel(const u64 *__restrict__ own, const u64 *__restrict__ opp,
                                                        int64_t n, Ctl *ctl)
 {
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     unsigned long long c = 0;
-    if (i < n) c = Dfs<R>::run(own[i], opp[i]);
+    if (i < n) c = Dfs<R>::run(own[i], opp[i], rays);
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->leaves, c);
 }

@@ -10,17 +10,8 @@ using ob::u32;
 
 constexpr int kThreads = 128;
 
-// ray masks for obf::flips_for, [direction][square] so that lanes with different squares spread
-// over the shared-memory banks (2 KB per CTA)
-struct Rays {
-    const u64 *t;
-    __device__ __forceinline__ u64 operator()(int d, int s) const { return t[d * 64 + s]; }
-};
-
-__device__ __forceinline__ void fill_rays(u64 *t)
-{
-    for (int i = threadIdx.x; i < obf::kRayDirs * 64; i += blockDim.x) t[i] = obf::make_ray(i >> 6, i & 63);
-}
+using ob::Rays;
+using ob::fill_rays;
 
 // w[phase] . (mobility, a..h) + w[phase][9] with the tuned move generator
 __device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__restrict__ w)

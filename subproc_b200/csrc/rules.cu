@@ -1,7 +1,7 @@
 // rules.cu -- batched Board rules, features and linear evaluation on explicit positions.
 //
 // One thread per position; loads and stores are unit-stride (SoA arrays of u64 / u8 / i32),
-// everything between them is register arithmetic from bitboard.cuh.
+// everything between them is register arithmetic from fastboard.cuh / bitboard.cuh.
 #include "common.cuh"
 
 using namespace ob;
@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(kThreads) legal_kernel(const u64 *__restrict__
                                                          u64 *__restrict__ legal, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) legal[i] = legal_moves(own[i], opp[i]);
+    if (i < n) legal[i] = obf::legal_moves(own[i], opp[i]);
 }
 
 // Board.put(piece, x, y) flip set (board.py:161-174)
@@ -23,6 +23,10 @@ __global__ void __launch_bounds__(kThreads) flips_kernel(const u64 *__restrict__
                                                          const uint8_t *__restrict__ square, u64 *__restrict__ flips,
                                                          int64_t n)
 {
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const u64 a = own[i], b = opp[i];
@@ -30,7 +34,7 @@ __global__ void __launch_bounds__(kThreads) flips_kernel(const u64 *__restrict__
     u64 f = 0;
     if (s < 64) {
         const u64 x = 1ull << s;
-        if (!((a | b) & x)) f = flips_for(x, a, b);           // occupied => put returns 0 (board.py:162-163)
+        if (!((a | b) & x)) f = put_flips((int)s, a, b, rays);   // occupied => put returns 0 (board.py:162-163)
     }
     flips[i] = f;
 }
@@ -42,6 +46,10 @@ __global__ void __launch_bounds__(kThreads) step_kernel(u64 *__restrict__ black,
                                                         int32_t *__restrict__ ret, uint8_t *__restrict__ flags,
                                                         int64_t n)
 {
+    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    fill_rays(ray_s);
+    __syncthreads();
+    const Rays rays = {ray_s};
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     u64 b = black[i], w = white[i];
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(u64 *__restrict__ black,
         out = 0;                                              // 'ps'/'PS' is never validated (board.py:194-195)
     } else if (mv < 64) {
         const u64 x = 1ull << mv;
-        if (!((own | opp) & x)) f = flips_for(x, own, opp);
+        if (!((own | opp) & x)) f = put_flips((int)mv, own, opp, rays);
         const int c = __popcll(f);
         if (c) { out = c; own |= f | x; opp &= ~f; }          // put() == 0 => -1, state untouched (board.py:199-201)
     }
@@ -73,8 +81,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(u64 *__restrict__ black,
         const bool bm = (t == OTHELLO_BLACK);
         const u64 mover = bm ? b : w, other = bm ? w : b;
         uint8_t fl = 0;
-        if (legal_moves(mover, other) == 0)
-            fl = legal_moves(other, mover) == 0 ? OTHELLO_F_GAME_OVER : OTHELLO_F_MUST_PASS;
+        if (obf::legal_moves(mover, other) == 0)
+            fl = obf::legal_moves(other, mover) == 0 ? OTHELLO_F_GAME_OVER : OTHELLO_F_MUST_PASS;
         flags[i] = fl;
     }
 }
