@@ -12,9 +12,10 @@ step).  Games are independent, so N GPUs run N shards with no data-path collecti
     e2e     = the same through the host-buffer C ABI (othello_playout_host): start positions come
               from pinned host memory, per-game results (plies, final position) go back to host
               memory, trajectories stay in HBM -- copies inside the timed region
-    roofline= integer-ALU roofline of the playout kernel: 512 INT32 lane-ops per position-step
-               against the INT32 ALU peak measured live by csrc/peak.cu, plus the
-              HBM write-out rate (17 B per position) against MEASURED_PEAKS.json
+    roofline= integer roofline of the playout kernel: 512 INT32 lane-ops per position-step
+               against the integer peak measured live by csrc/peak.cu (ALU + FMA pipes
+              co-issuing LOP3 + IMAD; the ALU-pipe-only peak is reported next to it), plus the HBM
+              write-out rate (17 B per position) against MEASURED_PEAKS.json
     cpu_baseline = the reference's own board.py (oracle/_ref, py3 transcription) playing the same
               kind of games on all host cores for a bounded time (N=1, rank 0 only)
 
@@ -249,7 +250,8 @@ def run_b200_arm(args):
 
     for i in range(W):
         one_step(i)
-    int_peak = ops.int32_peak(dev)                                         # lane-ops/s, measured on this GPU
+    int_peak_alu = ops.int32_peak(dev)                                     # ALU pipe alone (LOP3/SHF), lane-ops/s
+    int_peak = ops.int32_peak(dev, dual=True)                              # ALU + FMA pipes (LOP3 + IMAD): the integer ceiling
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -330,9 +332,11 @@ def run_b200_arm(args):
                        "l2": "kernel reads no input from HBM; ~%.2f GB written per step exceeds the 126 MB L2"
                              % (pos_per_launch * BYTES_PER_POSITION / 1e9),
                        "parallelism": "games sharded over %d GPU(s), no data-path collective" % n_gpus},
-            "roofline": {"bound": "int32_alu", "achieved": achieved_ops / 1e12, "peak": int_peak / 1e12,
+            "roofline": {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tlane-op/s", "frac": achieved_ops / int_peak, "traffic": traffic,
-                         "peak_source": "csrc/peak.cu LOP3/SHF micro-benchmark, measured in this run",
+                         "peak_source": "csrc/peak.cu, measured in this run: LOP3 + IMAD co-issued on the ALU and FMA "
+                                        "pipes (the two pipes that execute 32-bit integer lane-ops)",
+                         "peak_alu_pipe_only": int_peak_alu / 1e12, "frac_alu_pipe_only": achieved_ops / int_peak_alu,
                          "algorithmic": "%d INT32 lane-ops per position-step (SURVEY.md 8d)" % LANE_OPS_PER_POSITION,
                          "kernel": "playout_kernel<random,traj>", "kernel_ms": kern_ms,
                          "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -182,6 +182,10 @@ int othello_unpack_keys(const uint64_t *keys, int32_t *features, int64_t n, void
  * denominator on the box.  sink: DEVICE uint32[blocks*threads]. */
 int othello_int32_peak_kernel(uint32_t *sink, int blocks, int threads, int iters, void *stream);
 
+/* Same, but every round is 16 LOP3 (ALU pipe) + 16 IMAD (FMA pipe): the integer ceiling of code that
+ * spreads its work over both pipes (32 lane-ops per thread per round). */
+int othello_int32_dual_peak_kernel(uint32_t *sink, int blocks, int threads, int iters, void *stream);
+
 /* ---- host-buffer front end (what a non-torch caller binds) ----------------------------------- */
 
 typedef struct othello_ctx othello_ctx;

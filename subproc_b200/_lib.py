@@ -56,6 +56,7 @@ SIGNATURES = {
     "othello_value_smooth": (ctypes.c_int, [vp, vp, vp, ctypes.c_double, vp, i64, vp]),
     "othello_unpack_keys": (ctypes.c_int, [vp, vp, i64, vp]),
     "othello_int32_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "othello_int32_dual_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "othello_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
     "othello_ctx_destroy": (None, [vp]),
     "othello_legal_host": (ctypes.c_int, [vp, vp, vp, vp, i64]),

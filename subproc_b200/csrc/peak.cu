@@ -34,7 +34,40 @@ __global__ void int32_peak_kernel(uint32_t *sink, int iters)
     sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// Both integer-capable pipes at once: per chain and round 2 LOP3 (ALU pipe) + 2 IMAD (FMA pipe), the
+// multiplier coming from a kernel argument so that ptxas cannot strength-reduce it.  This is the
+// ceiling for code that balances its integer work over the two pipes (what fastboard.cuh aims at).
+__global__ void int32_dual_peak_kernel(uint32_t *sink, int iters, uint32_t mul)
+{
+    uint32_t a[kChains], b[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; c++) {
+        a[c] = threadIdx.x * 2654435761u + c;
+        b[c] = blockIdx.x * 40503u + 7u * c + 1u;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < kChains; c++) {
+            a[c] = (a[c] & b[c]) ^ 0x9E3779B9u;                           // LOP3
+            b[c] = b[c] * mul + a[c];                                     // IMAD
+            a[c] = (a[c] | b[c]) ^ 0x7F4A7C15u;                           // LOP3
+            b[c] = b[c] * mul + a[c];                                     // IMAD
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < kChains; c++) acc ^= a[c] ^ b[c];
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace
+
+extern "C" int othello_int32_dual_peak_kernel(uint32_t *sink, int blocks, int threads, int iters, void *stream)
+{
+    OB_CHECK_ARGS(sink && blocks > 0 && threads > 0 && threads <= 1024 && iters >= 0);
+    int32_dual_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters, 2654435769u);
+    return ob_launch_status();
+}
 
 extern "C" int othello_int32_peak_kernel(uint32_t *sink, int blocks, int threads, int iters, void *stream)
 {

@@ -286,25 +286,27 @@ def learn_accumulate(po, stats=None, lam=0.90):
     return stats
 
 
-def int32_peak(device=None, iters=4096, blocks_per_sm=8, threads=256, repeats=5):
-    """Measured INT32 ALU-pipe throughput (lane-ops/s) of this GPU: the integer roofline denominator.
+def int32_peak(device=None, iters=4096, blocks_per_sm=8, threads=256, repeats=5, dual=False):
+    """Measured INT32 throughput (lane-ops/s) of this GPU: the integer roofline denominator.
 
-    One round of the micro-benchmark kernel (csrc/peak.cu) is 32 ALU-pipe lane-ops per thread.
+    dual=False: ALU pipe only (LOP3/SHF); dual=True: ALU + FMA pipes (LOP3 + IMAD, 1:1).  One round
+    of either micro-benchmark kernel (csrc/peak.cu) is 32 integer lane-ops per thread.
     """
     device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     blocks = sms * blocks_per_sm
     sink = torch.empty(blocks * threads, dtype=torch.int32, device=device)
     L = _lib.lib()
+    kern = L.othello_int32_dual_peak_kernel if dual else L.othello_int32_peak_kernel
     best = None
     with torch.cuda.device(device):
         st = _stream(sink)
         for _ in range(2):
-            _lib.check(L.othello_int32_peak_kernel(ctypes.c_void_p(sink.data_ptr()), blocks, threads, iters, st), "peak")
+            _lib.check(kern(ctypes.c_void_p(sink.data_ptr()), blocks, threads, iters, st), "peak")
         for _ in range(repeats):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(L.othello_int32_peak_kernel(ctypes.c_void_p(sink.data_ptr()), blocks, threads, iters, st), "peak")
+            _lib.check(kern(ctypes.c_void_p(sink.data_ptr()), blocks, threads, iters, st), "peak")
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1)
