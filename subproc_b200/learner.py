@@ -98,6 +98,30 @@ def shard_of_games(total_games, rank, world):
     return lo, min(lo + per, total_games)
 
 
+def batch_stats(black_discs, white_discs, black_name='black', white_name='white', params_used=''):
+    """The payload of LearnBasePlus.store_batch_stats (learn_base.py:58-110) from the final disc counts
+    of a batch of games, in book order.
+
+    Kept to the letter, including the reference's white-win test ``white_discs > black_wins``
+    (learn_base.py:77 compares White's discs with the running COUNT of Black wins); the count a reader
+    would expect is returned under 'white_wins_by_discs'."""
+    b = np.asarray(black_discs, dtype=np.int64)
+    w = np.asarray(white_discs, dtype=np.int64)
+    n = len(b)
+    black_won = b > w
+    wins_before = np.cumsum(black_won) - black_won           # black_wins when the elif is evaluated
+    white_won_ref = (~black_won) & (w > wins_before)
+    diff = (b - w).tolist()
+    return {
+        black_name + '_win_rate': float(black_won.sum()) / float(n),
+        white_name + '_win_rate': float(white_won_ref.sum()) / float(n),
+        'min_disc_diff': min(diff), 'max_disc_diff': max(diff),
+        'avg_disc_diff': float(sum(diff)) / float(n),
+        'params_used': params_used, 'diffs': sorted(diff),
+        'white_wins_by_discs': int((w > b).sum()),
+    }
+
+
 class ProgressPositionMovesLearn(object):
     """The reference learner's public surface (name / configure / fit_parameter / read_parameters,
     learn_base.py:8-33, progress_position_moves_learn.py:19-35) over on-GPU self-play."""
@@ -131,6 +155,12 @@ class ProgressPositionMovesLearn(object):
 
     def weights_table(self):
         return self.parameter.weights_table(self.read_parameters())
+
+    def store_batch_stats(self, playout, black_name='b200', white_name='b200', params_used='No Hamlet'):
+        """win rates / disc differences of a batch (learn_base.py:58-110), counts from the GPU"""
+        c = playout.final_counts().cpu().numpy()
+        self.last_batch_stats = batch_stats(c[:, 0], c[:, 1], black_name, white_name, params_used)
+        return self.last_batch_stats
 
     # ---- one learning iteration ------------------------------------------------------------
     def accumulate(self, playout, stats=None):

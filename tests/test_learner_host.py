@@ -135,3 +135,24 @@ def test_world_size_2_allreduce_equals_single_process_fit():
         flat = np.array(rows).reshape(-1)
         assert all(abs(flat[i] - round(flat[i])) < 1e-6 for i in np.flatnonzero(diff[1:]))
     assert got[0][1] == got[1][1]                                          # every rank ends with identical parameters
+
+
+def test_batch_stats_payload_follows_the_reference_loop():
+    rng = np.random.RandomState(8)
+    b = rng.randint(0, 65, size=300)
+    w = 64 - b - rng.randint(0, 3, size=300)
+    w = np.maximum(w, 0)
+    # learn_base.py:58-98, restated literally
+    black_wins = white_wins = 0
+    diff = []
+    for bd, wd in zip(b, w):
+        diff.append(int(bd - wd))
+        if bd > wd:
+            black_wins += 1
+        elif wd > black_wins:
+            white_wins += 1
+    got = learner.batch_stats(b, w, 'A', 'B', 'p')
+    assert got['A_win_rate'] == float(black_wins) / 300 and got['B_win_rate'] == float(white_wins) / 300
+    assert got['min_disc_diff'] == min(diff) and got['max_disc_diff'] == max(diff)
+    assert got['avg_disc_diff'] == float(sum(diff)) / 300 and got['diffs'] == sorted(diff) and got['params_used'] == 'p'
+    assert got['white_wins_by_discs'] == int((w > b).sum())
