@@ -125,3 +125,36 @@ class ProgressPositionMovesParameter(ParameterBasePlus):    # parameter_progress
         w = np.zeros((4, 10), dtype=np.float32)
         w[:, :9] = rows
         return w
+
+
+def counts_from_engine(a_book, side, path):
+    """parameter_learn_from_edax_protocol.counts (:7-13): ask an external engine for the features of a
+    position -- ``<path> -h "<64 chars> <turn>"`` prints a Python list literal -- and prepend the disc
+    count.  Works with any engine that implements the switch, e.g.
+    ``python -m subproc_b200.edax_engine``.  (``side`` is ignored, as in the reference: the engine sees
+    only the position and whose turn it is.)"""
+    import subprocess
+    from ast import literal_eval
+    a_board = board_from_a_book(a_book)
+    sfen = a_board.serialize_str()
+    out = subprocess.check_output((path + " -h \"%s\"") % sfen, shell=True, universal_newlines=True)
+    discs = 64 - a_book['book'].count('-')
+    return [discs] + [int(x) for x in literal_eval(out.strip())]
+
+
+class LearnFromEdaxProtocolProcessParameter(ProgressPositionMovesParameter):
+    """parameter_learn_from_edax_protocol.py:16-39: same table, header 3, features from an engine process
+    named by ``learn_learn_for_path``"""
+
+    def __init__(self):
+        super(LearnFromEdaxProtocolProcessParameter, self).__init__()
+        self.conf = None
+
+    def configure(self, conf):
+        self.conf = conf
+
+    def header(self):
+        return 3
+
+    def hash_from_book(self, a_book, side):
+        return ':'.join(str(x) for x in counts_from_engine(a_book, side, self.conf['learn_learn_for_path']))

@@ -126,3 +126,16 @@ def test_do_match_with_plugin_recorders(tmp_path, golden_games):
     assert isinstance(rec, recorder.MemoryRecorder)
     won = match.do_match(conf, seed=5)
     assert won[0] in ('Black', 'White', 'None')
+
+
+def test_features_through_the_engine_process_parameter_class(golden_games):
+    """LearnFromEdaxProtocolProcessParameter shells out to `<engine> -h "<sfen>"` like the reference
+    (parameter_learn_from_edax_protocol.py:7-13,35-39); our engine answers with the GPU features"""
+    from subproc_b200 import parameter
+    P = parameter.LearnFromEdaxProtocolProcessParameter()
+    P.configure({'learn_learn_for_path': "cd %s && %s -m subproc_b200.edax_engine" % (ROOT, sys.executable)})
+    assert P.header() == 3
+    p = golden_games[0]['positions'][17]
+    bk = {'book': p['ser'][:64], 'whosturn': p['ser'][65], 'turn': p['nturn']}
+    want = p['feat_O'] if p['ser'][65] == 'O' else p['feat_X']
+    assert P.hash_from_book(bk, 'O') == ':'.join(str(v) for v in want)

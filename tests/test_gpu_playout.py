@@ -119,6 +119,9 @@ def test_perft_known_answers(oracle):
     want = [1, 4, 12, 56, 244, 1396, 8200, 55092, 390216, 3005288, 24571284]
     for d, v in enumerate(want):
         assert ops.perft(d, device=DEV) == v, d
+    # published Othello perft values beyond the survey's table (same counting convention)
+    assert ops.perft(11, device=DEV) == 212258800
+    assert ops.perft(12, device=DEV) == 1939886636
 
 
 def test_perft_other_roots_against_oracle(oracle):
