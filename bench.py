@@ -47,9 +47,10 @@ def _cpu_worker(args):
     """plays seeded random games (bare loop: puttables -> choose -> put_s -> is_game_over) until the
     deadline; returns (plies, games).  Runs in a multiprocessing worker."""
     kind, seed, gid0, budget_s, max_games = args
+    full_path = kind == "reference_full"
     t_end = time.perf_counter() + budget_s
     plies = games = 0
-    if kind == "reference":
+    if kind.startswith("reference"):
         from oracle import refshim, make_golden as mg
         rb = refshim.load().board
         while time.perf_counter() < t_end and games < max_games:
@@ -63,6 +64,12 @@ def _cpu_worker(args):
                     B.put_s(B.handstr_from_coord(x, y))
                 else:
                     B.put_s('ps')
+                if full_path:
+                    # what play_a_turn adds per ply (game_runner.py:154-163 + RedisRecorder.add,
+                    # game_recorder.py:107-114): the printed board, the serialised record, its end flag
+                    str(B)
+                    {'book': B.serialize_board(), 'whosturn': B.serialize_turn(), 'turn': B.nturn,
+                     'end': B.is_game_over()}
                 t += 1
             plies += t
             games += 1
@@ -75,8 +82,9 @@ def _cpu_worker(args):
     return plies, games
 
 
-def cpu_baseline(budget_s=12.0, max_games_per_worker=1 << 30, seed=1):
-    """reference CPU path on all host cores for ~budget_s seconds."""
+def cpu_baseline(budget_s=12.0, max_games_per_worker=1 << 30, seed=1, full_path_s=0.0):
+    """reference CPU path on all host cores for ~budget_s seconds (+ full_path_s seconds of the
+    play_a_turn-equivalent path, reported separately)."""
     import multiprocessing as mp
     from oracle import refshim
     kind = "reference" if refshim.available() else "port"
@@ -93,8 +101,20 @@ def cpu_baseline(budget_s=12.0, max_games_per_worker=1 << 30, seed=1):
     games = sum(r[1] for r in res)
     what = ("reference board.py (oracle/_ref py3 transcription)" if kind == "reference"
             else "oracle/othello_oracle.c port (reference not present on this box)")
+    extra = {}
+    if kind == "reference" and full_path_s > 0:
+        t1 = time.perf_counter()
+        with ctx.Pool(cores) as pool:
+            res2 = pool.map(_cpu_worker, [("reference_full", seed, w * (1 << 24), full_path_s, max_games_per_worker)
+                                          for w in range(cores)])
+        dt2 = time.perf_counter() - t1
+        extra = {"full_play_a_turn_path": {"value": sum(r[0] for r in res2) / dt2, "unit": UNIT,
+                                           "games_per_s": sum(r[1] for r in res2) / dt2,
+                                           "what": "adds str(board), recorder-style serialisation and its "
+                                                   "is_game_over per ply (game_runner.py:154-163, "
+                                                   "game_recorder.py:107-114), %.1f s" % dt2}}
     return {"value": plies / dt, "unit": UNIT, "cores": cores, "kind": kind,
-            "games_per_s": games / dt,
+            "games_per_s": games / dt, **extra,
             "sample": "%d random-playout games (%d plies) from the standard opening, bare loop "
                       "puttables->choose->put_s->is_game_over, %s, multiprocessing.Pool(%d), %.1f s"
                       % (games, plies, what, cores, dt)}, dt
@@ -224,7 +244,7 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the hot path is sm_100a kernels, there is no CPU fallback")
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(budget_s=args.cpu_seconds)          # before CUDA is initialised (fork-safe)
+        cb, _ = cpu_baseline(budget_s=args.cpu_seconds, full_path_s=args.cpu_seconds / 2)   # before CUDA is initialised (fork-safe)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
