@@ -1,0 +1,60 @@
+"""Multi-GPU path on a box with >= 2 B200s: one process per GPU over NCCL.  Games shard
+by global game id with no data-path collective; the learner's only exchange is one all-reduce of the
+[4][112] statistics.  Skipped on single-GPU boxes (the CPU suite covers the same logic over gloo)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WORLD = 2
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from subproc_b200 import ops, learner, parameter
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    total = 8192
+    lo, hi = learner.shard_of_games(total, rank, world)
+    w = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(dev)
+    po = ops.playout(hi - lo, seed=17, gid0=lo, device=dev, policy=ops.POLICY_GREEDY, random_plies=10, weights=w)
+    stats = ops.learn_accumulate(po)
+    L = learner.ProgressPositionMovesLearn()
+    rows = L.learn_from_stats(stats)                             # all-reduce inside
+    q.put((rank, po.nplies.cpu().numpy(), ops.bits_numpy(po.final_black), stats.cpu().numpy(), L.read_parameters()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < WORLD, reason="needs >= 2 GPUs")
+def test_two_ranks_equal_one_gpu_on_the_union_of_games():
+    import torch.multiprocessing as mp
+    from subproc_b200 import ops, learner, parameter
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, WORLD, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=300) for _ in range(WORLD)), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    w = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(dev)
+    po = ops.playout(8192, seed=17, gid0=0, device=dev, policy=ops.POLICY_GREEDY, random_plies=10, weights=w)
+    assert np.array_equal(np.concatenate([g[1] for g in got]), po.nplies.cpu().numpy())          # same games, sharded
+    assert np.array_equal(np.concatenate([g[2] for g in got]), ops.bits_numpy(po.final_black))
+    whole = ops.learn_accumulate(po).cpu().numpy()
+    for g in got:                                                  # every rank holds the all-reduced statistics
+        assert np.array_equal(g[3][:, :100], whole[:, :100]) and np.array_equal(g[3][:, 110], whole[:, 110])
+        assert np.allclose(g[3], whole, rtol=1e-9, atol=1e-9)
+    assert got[0][4] == got[1][4]                                  # identical parameters on all ranks
+    L = learner.ProgressPositionMovesLearn()
+    L.learn_from_stats(torch.from_numpy(whole))
+    assert max(abs(a - b) for a, b in zip(L.read_parameters(), got[0][4])) <= 1
