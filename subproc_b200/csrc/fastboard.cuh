@@ -149,7 +149,7 @@ OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp
 // ---- put(): flips through carry propagation along rays -----------------------------------------
 // ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge
 constexpr int kRayDirs = 4;
-OBF_HD u64 make_ray(int d, int s)
+OBF_HD constexpr u64 make_ray(int d, int s)
 {
     const int dx = (d == 0) ? 1 : (d == 1) ? -1 : (d == 2) ? 0 : 1;   // +1: E, +7: SW, +8: S, +9: SE (y grows with s)
     const int dy = (d == 0) ? 0 : 1;
