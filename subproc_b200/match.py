@@ -30,13 +30,15 @@ def engine_from_spec(spec):
     raise ValueError("unknown engine spec %r (expected random | greedy | greedy:<param file>)" % spec)
 
 
-def do_match(conf, seed=0, device=None):                 # subproc.py:15-39
-    proc_a = {"path": conf['proc_a_path'], "n_rand_hands": conf.get('proc_n_rand_hands_for_a', 0)}
-    proc_b = {"path": conf['proc_b_path'], "n_rand_hands": conf.get('proc_n_rand_hands_for_b', 0)}
-    debug = conf.get('proc_debug', 0) == 1
+def do_match(conf, seed=0, device=None):
+    """One match as configured (the job of subproc.py:15-39): engines and substitution budgets per side,
+    optional colour swap, recorder plugin opened as a context manager, one game played."""
+    sides = [(engine_from_spec(conf['proc_%s_path' % k]), int(conf.get('proc_n_rand_hands_for_%s' % k, 0)))
+             for k in ('a', 'b')]
     if conf.get('proc_randomize_black_white', 0) == 1 and random.randrange(2) == 1:
-        proc_a, proc_b = proc_b, proc_a
+        sides.reverse()                                   # "... and swapped black and white"
+    (black, n_black), (white, n_white) = sides
     with get_game_recorder(conf) as recorder:
-        gr = GameRunner(engine_from_spec(proc_a['path']), engine_from_spec(proc_b['path']), recorder, debug,
-                        proc_a['n_rand_hands'], proc_b['n_rand_hands'], device=device, seed=seed)
-        return gr.play_a_game()
+        runner = GameRunner(black, white, recorder, conf.get('proc_debug', 0) == 1, n_black, n_white,
+                            device=device, seed=seed)
+        return runner.play_a_game()
