@@ -191,6 +191,55 @@ class ProgressPositionMovesLearn(object):
             self.last_processed_id = book_id
         return rows
 
+    # ---- the reference's book-driven entry point ---------------------------------------------
+    def learn_and_update_batch(self, books, device=None, sample=50000, seed=0):
+        """LearnBasePlus.learn_and_update_batch (progress_position_moves_learn.py:88-101) on the
+        reference's own input: ``books`` = [(book_id, records, meta)] with ``records`` as learn_books
+        hands them over -- sorted by turn and REVERSED, records[0] the terminal position
+        (replearn.py:37-38).  Every (record, side) updates the value table in the reference's order
+        (:37-48), then the four shards are refitted on samples of the table (:115-158 -> value_table.
+        fit_parameter) and stored with int() truncation (:196-209).  Returns (mses, scores, params,
+        nsamples) like __fit_parameters."""
+        import torch
+        from . import books as books_mod
+        from . import ops, value_table
+        dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        if getattr(self, 'table', None) is None:
+            self.table = value_table.ValueTable(device=dev, a=self.a, lam=self.l)
+        flat, targets = [], []
+        last_book_id = -1
+        for book_id, records, _meta in books:
+            last_turn = int(records[0]['turn'])
+            flat.extend(records)
+            targets.append((len(records), last_turn, [int(r['turn']) for r in records]))
+            last_book_id = book_id
+        if flat:
+            black, white, _who, _turns = books_mod.positions_from_books(flat, device=dev)
+            n = black.numel()
+            side_o = torch.full((n,), ops.BLACK, dtype=torch.uint8, device=dev)
+            fo = ops.features(black, white, side_o).cpu().numpy()
+            fx = ops.features(black, white, side_o + 1).cpu().numpy()
+            keys = np.empty(2 * n, dtype=np.int64)
+            vals = np.empty(2 * n, dtype=np.float64)
+            at = 0
+            for count, last_turn, turns in targets:
+                nb, nw = int(fo[at, 2:].sum()), int(fx[at, 2:].sum())          # records[0] is terminal: its disc counts
+                for j in range(count):
+                    left = last_turn - turns[j]
+                    keys[2 * (at + j)] = value_table.pack_key(fo[at + j])
+                    vals[2 * (at + j)] = float(nb - nw) * (self.l ** left)     # side 'O', value_for_black (:40-47)
+                    keys[2 * (at + j) + 1] = value_table.pack_key(fx[at + j])
+                    vals[2 * (at + j) + 1] = float(nw - nb) * (self.l ** left)
+                at += count
+            self.table.update(torch.from_numpy(keys).to(dev), torch.from_numpy(vals).to(dev))
+        mses, scores, params, nsamples = [], [], [], []
+        for s, (lo, hi) in enumerate(PHASE_SHARDS):
+            mse, score, param, nsample = self.table.fit_parameter(lo, hi, num=sample, seed=seed + s)
+            mses.append(mse); scores.append(score); params.append(param); nsamples.append(nsample)
+        self.params = stored_parameters(params)
+        self.last_processed_id = last_book_id
+        return mses, scores, params, nsamples
+
     def self_play_iteration(self, games_per_rank, seed=0, iteration=0, random_plies=10, device=None, rank=0,
                             world=1, t_max=120):
         """config 5: greedy self-play with the current weights on this rank's shard of game ids,

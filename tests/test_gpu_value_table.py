@@ -56,3 +56,28 @@ def test_table_fit_runs_and_scales_like_the_reference():
     assert mse > 0 and score <= 1
     f = vt.features().cpu().numpy()
     assert f[:, 0].min() >= 4 and f[:, 0].max() <= 64 and (f[:, 2:].sum(axis=1) <= f[:, 0]).all()
+
+
+def test_book_driven_learn_and_update_batch_equals_trajectory_path(oracle):
+    """the reference's entry point (books in the recorder schema, reversed, terminal first) must build
+    the same table as the trajectory path, and refit parameters from it"""
+    from subproc_b200 import books, learner
+    n = 40
+    po = ops.playout(n, seed=33, gid0=0, device=DEV)
+    vt = value_table.ValueTable(device=DEV)
+    vt.update_from_playout(po)
+    bks = []
+    for i, (recs, meta) in enumerate(books.books_from_playout(po)):
+        rev = list(reversed(sorted(recs, key=lambda r: int(r['turn']))))        # learn_books, replearn.py:37-38
+        assert rev[0]['end']
+        bks.append((i + 1, rev, meta))
+    L = learner.ProgressPositionMovesLearn()
+    L.configure({})
+    mses, scores, params, nsamples = L.learn_and_update_batch(bks, device=DEV, sample=2000)
+    assert L.table.items() == vt.items()                                        # bit-identical values, same keys
+    assert L.last_processed() == n and len(params) == 4 and all(len(p) == 9 for p in params)
+    rp = L.read_parameters()
+    assert rp[0] == 2 and len(rp) == 37 and all(-127 <= v <= 127 for v in rp[1:])
+    stats = L.store_batch_stats(po)
+    c = po.final_counts().cpu().numpy()
+    assert stats['min_disc_diff'] == int((c[:, 0] - c[:, 1]).min()) and len(stats['diffs']) == n
