@@ -301,7 +301,7 @@ def run_b200_arm(args):
 
     def e2e_step(i):
         _lib.check(L.othello_playout_host(ctx, 1, gid_base + (W + K + i) * G, G, P(h_b0), P(h_w0), P(h_t0),
-                                          ops.POLICY_RANDOM, 0, 0, 0, None, T_MAX, None, None, None,
+                                          ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX, None, None, None,
                                           P(h_np), P(h_fb), P(h_fw)), "othello_playout_host")
         return int(h_np.sum(dtype=torch.int64).item())
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OTHELLO_ABI_VERSION 1
+#define OTHELLO_ABI_VERSION 2
 
 #define OTHELLO_EMPTY 0
 #define OTHELLO_BLACK 1
@@ -128,6 +128,10 @@ typedef struct {
     int32_t  *nplies;             /* [n] plies played, passes included (= nturn of the terminal position) */
     uint64_t *final_black;        /* [n] terminal position */
     uint64_t *final_white;
+    /* proc_black / proc_white may be different engines (GameRunner.__init__, game_runner.py:107-123): */
+    int32_t  policy_white;        /* White's engine, or -1 = the same as `policy` (which is then both players') */
+    int32_t  reserved;
+    const float *weights_white;   /* DEVICE float[4][10] for White's greedy engine, or NULL = `weights` */
 } othello_playout_args;
 
 int othello_playout(const othello_playout_args *args, void *stream);
@@ -204,7 +208,8 @@ int othello_step_host(othello_ctx *ctx, uint64_t *black, uint64_t *white, uint8_
 int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t n_games,
                          const uint64_t *black0, const uint64_t *white0, const uint8_t *turn0,
                          int32_t policy, int32_t random_plies, int32_t n_rand_black, int32_t n_rand_white,
-                         const float *weights /* host [4][10] or NULL */, int32_t t_max,
+                         const float *weights /* host [4][10] or NULL */, int32_t policy_white /* -1 = same */,
+                         const float *weights_white /* host [4][10] or NULL = same */, int32_t t_max,
                          uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move /* host or NULL */,
                          int32_t *nplies, uint64_t *final_black, uint64_t *final_white);
 

@@ -63,8 +63,8 @@ def lib():
         L.orc_playout_batch.argtypes = [
             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64,
             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8),
-            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-            ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int64,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int64,
             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8),
             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         for name in ("orc_puttables_batch", "orc_game_over_batch", "orc_step_batch", "orc_put_batch",
@@ -177,7 +177,8 @@ def rng_draw(key, ply, stream):
 
 
 def playout(seed, gid0, n, black0=None, white0=None, turn0=None, policy=POLICY_RANDOM, random_plies=0,
-            n_rand_black=0, n_rand_white=0, weights=None, t_max=120, trajectory=True):
+            n_rand_black=0, n_rand_white=0, weights=None, t_max=120, trajectory=True, policy_white=None,
+            weights_white=None):
     """Play games gid0..gid0+n-1 (GameRunner.play_a_game, game_runner.py:165-201).
 
     Returns dict(black[t_max+1][n], white[t_max+1][n], move[t_max][n], nplies[n], final_black[n],
@@ -185,6 +186,8 @@ def playout(seed, gid0, n, black0=None, white0=None, turn0=None, policy=POLICY_R
     """
     w = np.ascontiguousarray(np.asarray(DEFAULT_WEIGHTS if weights is None else weights,
                                         dtype=np.float64).reshape(4, 10))
+    ww = w if weights_white is None else np.ascontiguousarray(np.asarray(weights_white, dtype=np.float64).reshape(4, 10))
+    pw = policy if policy_white is None else policy_white
     b0 = _u64(black0) if black0 is not None else None
     w0 = _u64(white0) if white0 is not None else None
     t0 = _u8(turn0, n) if turn0 is not None else None
@@ -196,8 +199,8 @@ def playout(seed, gid0, n, black0=None, white0=None, turn0=None, policy=POLICY_R
     fw = np.zeros(n, dtype=np.uint64)
     lib().orc_playout_batch(ctypes.c_uint64(seed), ctypes.c_uint64(gid0), ctypes.c_int64(n),
                             _p(b0, ctypes.c_uint64), _p(w0, ctypes.c_uint64), _p(t0, ctypes.c_uint8),
-                            policy, random_plies, n_rand_black, n_rand_white,
-                            _p(w, ctypes.c_double), t_max, ctypes.c_int64(n),
+                            policy, pw, random_plies, n_rand_black, n_rand_white,
+                            _p(w, ctypes.c_double), _p(ww, ctypes.c_double), t_max, ctypes.c_int64(n),
                             _p(tb, ctypes.c_uint64), _p(tw, ctypes.c_uint64), _p(mv, ctypes.c_uint8),
                             _p(nplies, ctypes.c_int32), _p(fb, ctypes.c_uint64), _p(fw, ctypes.c_uint64))
     return dict(black=tb, white=tw, move=mv, nplies=nplies, final_black=fb, final_white=fw)

@@ -121,7 +121,8 @@ def engine_answer(ns, B, puttables, greedy, r1, rows):
     return B.handstr_from_coord(*best)
 
 
-def play_game(ns, seed, gid, policy, random_plies, n_rand_black, n_rand_white, rows, record_features):
+def play_game(ns, seed, gid, policy, random_plies, n_rand_black, n_rand_white, rows, record_features,
+              policy_white=None, rows_white=None):
     """GameRunner.play_a_game / play_a_turn / go_for (game_runner.py:133-184) on the reference Board."""
     rb = ns.board
     B = rb.Board()
@@ -154,7 +155,10 @@ def play_game(ns, seed, gid, policy, random_plies, n_rand_black, n_rand_white, r
                 hand = B.handstr_from_coord(x, y)
                 rest[B.turn] -= 1
         if hand is None:
-            hand = engine_answer(ns, B, puttables, policy == 1 and t >= random_plies, r1, rows).lower()
+            # proc_black and proc_white may be different engines (game_runner.py:107-123)
+            pol = policy if (B.turn == rb.Black or policy_white is None) else policy_white
+            rws = rows if (B.turn == rb.Black or rows_white is None) else rows_white
+            hand = engine_answer(ns, B, puttables, pol == 1 and t >= random_plies, r1, rws).lower()
         before = bits(rb, B)
         mover = B.turn
         ret = B.put_s(hand)
@@ -171,9 +175,14 @@ def play_game(ns, seed, gid, policy, random_plies, n_rand_black, n_rand_white, r
         snap()
         t += 1
         over = B.is_game_over()
-    return {'seed': seed, 'gid': gid, 'policy': policy, 'random_plies': random_plies,
-            'n_rand_black': n_rand_black, 'n_rand_white': n_rand_white,
-            'plies': plies, 'positions': positions}
+    out = {'seed': seed, 'gid': gid, 'policy': policy, 'random_plies': random_plies,
+           'n_rand_black': n_rand_black, 'n_rand_white': n_rand_white,
+           'plies': plies, 'positions': positions}
+    if policy_white is not None:
+        out['policy_white'] = policy_white
+    if rows_white is not None:
+        out['rows_white'] = rows_white
+    return out
 
 
 def perft(rb, B, depth):
@@ -336,6 +345,12 @@ def main():
         games.append(play_game(ns, 2, gid, 1, 10, 0, 0, rows, record_features=False))
     for gid in range(4):                                        # greedy engine + reference substitution rule
         games.append(play_game(ns, 3, gid, 1, 0, 10, 2, rows, record_features=False))
+    other = [[3, 80, 40, -20, 5, 5, 1, 1, 2], [10, 60, 30, -10, 4, 6, 2, 2, 1],
+             [20, 50, 20, -5, 3, 7, 3, 3, 3], [64, 10, 10, 10, 10, 10, 10, 10, 10]]
+    for gid in range(3):                                        # different engines per colour: greedy vs random
+        games.append(play_game(ns, 4, gid, 1, 2, 0, 0, rows, False, policy_white=0))
+    for gid in range(3):                                        # two greedy engines with different parameter sets
+        games.append(play_game(ns, 5, gid, 1, 4, 1, 1, rows, False, policy_white=1, rows_white=other))
     dump("games.json.gz", games)
     dump("probe.json.gz", make_probe(ns, games))
     dump("paramgen.json.gz", make_paramgen())

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libothello_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -31,6 +31,7 @@ class PlayoutArgs(ctypes.Structure):
         ("weights", vp), ("t_max", i32), ("stride", i64),
         ("traj_black", vp), ("traj_white", vp), ("traj_move", vp),
         ("nplies", vp), ("final_black", vp), ("final_white", vp),
+        ("policy_white", i32), ("reserved", i32), ("weights_white", vp),
     ]
 
 
@@ -62,7 +63,7 @@ SIGNATURES = {
     "othello_legal_host": (ctypes.c_int, [vp, vp, vp, vp, i64]),
     "othello_step_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
     "othello_playout_host": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32, i32,
-                                            vp, i32, vp, vp, vp, vp, vp, vp]),
+                                            vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     "othello_ctx_trajectory": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                               ctypes.POINTER(i64), ctypes.POINTER(i32)]),
 }

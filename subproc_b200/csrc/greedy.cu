@@ -28,7 +28,7 @@ struct WarpScratch {
     u64 own[32], opp[32];                     // positions of the 32 games (mover-relative)
     unsigned best_key[32];                    // arg-max state per game
     unsigned best_sq[32];
-    unsigned short item[kMaxItems];           // (game lane << 8) | square
+    unsigned short item[kMaxItems];           // (White to move << 15) | (game lane << 8) | square
 };
 
 // order-preserving map float -> u32 (larger float <=> larger unsigned); -0.0 is folded into +0.0
@@ -41,10 +41,18 @@ __device__ __forceinline__ unsigned ordered_bits(float v)
 template <bool SUBST, bool TRAJ>
 __global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_args a)
 {
-    __shared__ float w_s[OTHELLO_PHASES * OTHELLO_WEIGHTS];
+    constexpr int kW = OTHELLO_PHASES * OTHELLO_WEIGHTS;
+    __shared__ float w_s[2 * kW];                             // Black's table, then White's
     __shared__ u64 ray_s[obf::kRayDirs * 64];
     __shared__ WarpScratch scratch[kWarps];
-    if (threadIdx.x < OTHELLO_PHASES * OTHELLO_WEIGHTS) w_s[threadIdx.x] = a.weights[threadIdx.x];
+    if (threadIdx.x < 2 * kW) {
+        const float *src = threadIdx.x < kW ? (a.weights ? a.weights : a.weights_white)
+                                            : (a.weights_white ? a.weights_white : a.weights);
+        w_s[threadIdx.x] = src[threadIdx.x % kW];
+    }
+    // which colours are served by the greedy engine (the other answers uniformly at random)
+    const bool greedy_b = a.policy == OTHELLO_POLICY_GREEDY;
+    const bool greedy_w = (a.policy_white == -1 ? a.policy : a.policy_white) == OTHELLO_POLICY_GREEDY;
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_
         }
         const bool moving = !done && legal != 0;              // otherwise: finished, or this ply is a pass
         const int n = __popcll(legal);
-        bool random_now = t < a.random_plies;
+        bool random_now = t < a.random_plies || !(black_moves ? greedy_b : greedy_w);
         if (SUBST && moving) {
             if (substitute_now(key, t, black_moves ? rest_b : rest_w)) {           // game_runner.py:134-150
                 random_now = true;
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_
             if (evaluate) {
                 int idx = incl - cnt;
                 for (u64 rem = legal; rem; rem &= rem - 1)
-                    ws.item[idx++] = (unsigned short)((lane << 8) | (__ffsll((long long)rem) - 1));
+                    ws.item[idx++] = (unsigned short)((black_moves ? 0 : 0x8000) | (lane << 8) | (__ffsll((long long)rem) - 1));
             }
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
@@ -120,10 +128,10 @@ __global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_
                 unsigned owner = 0, sq = 0, kbits = 0, before = 0;
                 if (have) {
                     const unsigned it = ws.item[j];
-                    owner = it >> 8; sq = it & 63u;
+                    owner = (it >> 8) & 31u; sq = it & 63u;
                     const u64 o = ws.own[owner], p = ws.opp[owner];
                     const u64 f = obf::flips_for((int)sq, o, p, obf::rev64(o), obf::rev64(p), rays);
-                    kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, w_s));
+                    kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, (it & 0x8000u) ? w_s + kW : w_s));
                     before = ws.best_key[owner];
                 }
                 __syncwarp();

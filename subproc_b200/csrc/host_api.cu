@@ -143,8 +143,8 @@ int othello_step_host(othello_ctx *c, uint64_t *black, uint64_t *white, uint8_t 
 
 int othello_playout_host(othello_ctx *c, uint64_t seed, uint64_t gid0, int64_t n, const uint64_t *black0,
                          const uint64_t *white0, const uint8_t *turn0, int32_t policy, int32_t random_plies,
-                         int32_t n_rand_black, int32_t n_rand_white, const float *weights, int32_t t_max,
-                         uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move, int32_t *nplies,
+                         int32_t n_rand_black, int32_t n_rand_white, const float *weights, int32_t policy_white,
+                         const float *weights_white, int32_t t_max, uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move, int32_t *nplies,
                          uint64_t *final_black, uint64_t *final_white)
 {
     OB_CHECK_ARGS(c && n >= 0 && t_max >= 0);
@@ -155,17 +155,18 @@ int othello_playout_host(othello_ctx *c, uint64_t seed, uint64_t gid0, int64_t n
     OB_CUDA(cudaSetDevice(c->device));
     const size_t row8 = align256((size_t)n * 8), row1 = align256((size_t)n);
     const size_t tb_bytes = align256((size_t)(t_max + 1) * n * 8), tm_bytes = align256((size_t)t_max * n + 1);
-    int rc = reserve(c, 4 * row8 + row1 + align256((size_t)n * 4) + 256 + 2 * tb_bytes + tm_bytes);
+    int rc = reserve(c, 4 * row8 + row1 + align256((size_t)n * 4) + 512 + 2 * tb_bytes + tm_bytes);
     if (rc) return rc;
     Carver k = {c->ws, 0};
     uint64_t *d_b0 = k.take<uint64_t>(n), *d_w0 = k.take<uint64_t>(n), *d_fb = k.take<uint64_t>(n), *d_fw = k.take<uint64_t>(n);
     uint8_t *d_t0 = k.take<uint8_t>(n);
     int32_t *d_np = k.take<int32_t>(n);
-    float *d_wt = k.take<float>(OTHELLO_PHASES * OTHELLO_WEIGHTS);
+    float *d_wt = k.take<float>(OTHELLO_PHASES * OTHELLO_WEIGHTS), *d_wt2 = k.take<float>(OTHELLO_PHASES * OTHELLO_WEIGHTS);
     uint64_t *d_tb = k.take<uint64_t>((size_t)(t_max + 1) * n), *d_tw = k.take<uint64_t>((size_t)(t_max + 1) * n);
     uint8_t *d_tm = k.take<uint8_t>((size_t)t_max * n + 1);
     cudaStream_t s = c->stream;
     if (weights) OB_CUDA(cudaMemcpyAsync(d_wt, weights, sizeof(float) * OTHELLO_PHASES * OTHELLO_WEIGHTS, cudaMemcpyHostToDevice, s));
+    if (weights_white) OB_CUDA(cudaMemcpyAsync(d_wt2, weights_white, sizeof(float) * OTHELLO_PHASES * OTHELLO_WEIGHTS, cudaMemcpyHostToDevice, s));
     OB_CUDA(cudaEventRecord(c->ready, s));
 
     // Games are independent, so the batch is cut into chunks whose copy-in, kernel and copy-out run
@@ -190,6 +191,7 @@ int othello_playout_host(othello_ctx *c, uint64_t seed, uint64_t gid0, int64_t n
         a.black0 = black0 ? d_b0 + c0 : nullptr; a.white0 = black0 ? d_w0 + c0 : nullptr; a.turn0 = turn0 ? d_t0 + c0 : nullptr;
         a.policy = policy; a.random_plies = random_plies; a.n_rand_black = n_rand_black; a.n_rand_white = n_rand_white;
         a.weights = weights ? d_wt : nullptr;
+        a.policy_white = policy_white; a.reserved = 0; a.weights_white = weights_white ? d_wt2 : nullptr;
         a.t_max = t_max; a.stride = n;
         a.traj_black = d_tb + c0; a.traj_white = d_tw + c0; a.traj_move = d_tm + c0;
         a.nplies = d_np + c0; a.final_black = d_fb + c0; a.final_white = d_fw + c0;

@@ -99,11 +99,14 @@ extern "C" int othello_playout(const othello_playout_args *args, void *stream)
     OB_CHECK_ARGS(a.nplies && a.final_black && a.final_white);
     OB_CHECK_ARGS((a.black0 == nullptr) == (a.white0 == nullptr));
     OB_CHECK_ARGS(a.policy == OTHELLO_POLICY_RANDOM || a.policy == OTHELLO_POLICY_GREEDY);
+    OB_CHECK_ARGS(a.policy_white == -1 || a.policy_white == OTHELLO_POLICY_RANDOM || a.policy_white == OTHELLO_POLICY_GREEDY);
+    const int policy_white = a.policy_white == -1 ? a.policy : a.policy_white;
     OB_CHECK_ARGS(a.policy != OTHELLO_POLICY_GREEDY || a.weights != nullptr);
+    OB_CHECK_ARGS(policy_white != OTHELLO_POLICY_GREEDY || a.weights != nullptr || a.weights_white != nullptr);
     OB_CHECK_ARGS(a.n_rand_black >= 0 && a.n_rand_white >= 0 && a.random_plies >= 0);
     if (a.traj_black || a.traj_white || a.traj_move)
         OB_CHECK_ARGS(a.traj_black && a.traj_white && a.traj_move && a.t_max >= 0 && a.stride >= a.n_games);
-    const bool greedy = a.policy == OTHELLO_POLICY_GREEDY;
+    const bool greedy = a.policy == OTHELLO_POLICY_GREEDY || policy_white == OTHELLO_POLICY_GREEDY;
     cudaStream_t s = (cudaStream_t)stream;
     if (greedy) return ob_launch_greedy(a, s);
     return launch(a, s);

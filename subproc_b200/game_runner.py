@@ -1,11 +1,10 @@
 """The reference's GameRunner (game_runner.py:105-201) over the lock-step playout kernel.
 
-The reference plays ONE game between two engine subprocesses; here both "engines" are policies
-evaluated inside the playout kernel, and ``play_games(n)`` plays n games in one launch.  The
+The reference plays ONE game between two engine subprocesses; here the "engines" are policies
+evaluated inside the playout kernels, and ``play_games(n)`` plays n games in one launch.  The
 constructor keeps the reference's argument order (game_runner.py:107): where the reference takes
-two shell commands, this takes two engine specs; mixing different engines per colour is not
-supported by the kernel (both players are served by the same policy), which covers self-play
-(eljem_task.py:9-20 runs the same binary on both sides).
+two shell commands, this takes two engine specs -- Black's and White's may differ (random vs greedy,
+or two greedy engines with different parameter sets), like proc_black / proc_white.
 
 The recorder protocol is the reference's: ``recorder.add(board)`` for the initial position and
 after every ply (game_runner.py:170,159), ``add_meta`` + ``store`` at the end (:186-192).  Boards
@@ -38,8 +37,6 @@ class GameRunner(object):
             proc_black = Engine(proc_black)
         if not isinstance(proc_white, Engine):
             proc_white = Engine(proc_white)
-        if (proc_black.policy, proc_black.random_plies) != (proc_white.policy, proc_white.random_plies):
-            raise ValueError("both players must use the same engine policy (self-play kernel)")
         self.proc_black, self.proc_white = proc_black, proc_white
         self.recorder = game_recorder
         self.debug = debug
@@ -48,19 +45,26 @@ class GameRunner(object):
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self.seed = seed
         self.next_gid = 0
-        self._weights = None
-        if proc_black.policy == 'greedy':
-            import numpy as np
-            w = np.asarray(proc_black.weights, dtype=np.float64).reshape(4, -1)
-            self._weights = ops.weights_tensor(w[:, :9], self.device, w[:, 9] if w.shape[1] > 9 else None)
+        greedy = [e for e in (proc_black, proc_white) if e.policy == 'greedy']
+        if len(greedy) == 2 and greedy[0].random_plies != greedy[1].random_plies:
+            raise ValueError("the two greedy engines must share random_plies (one opening length per game)")
+        self.random_plies = greedy[0].random_plies if greedy else 0
+        self._weights = [self._table(e) for e in (proc_black, proc_white)]
+
+    def _table(self, engine):
+        if engine.policy != 'greedy':
+            return None
+        import numpy as np
+        w = np.asarray(engine.weights, dtype=np.float64).reshape(4, -1)
+        return ops.weights_tensor(w[:, :9], self.device, w[:, 9] if w.shape[1] > 9 else None)
 
     def play_games(self, n_games, trajectory=True, t_max=ops.T_MAX_DEFAULT, out=None):
         """n_games games in one launch; returns an ops.Playout (trajectories stay in HBM)."""
-        po = ops.playout(n_games, seed=self.seed, gid0=self.next_gid, device=self.device,
-                         policy=ops.POLICY_GREEDY if self.proc_black.policy == 'greedy' else ops.POLICY_RANDOM,
-                         random_plies=self.proc_black.random_plies, n_rand_black=self.n_rand_black,
-                         n_rand_white=self.n_rand_white, weights=self._weights, t_max=t_max,
-                         trajectory=trajectory, out=out)
+        pol = [ops.POLICY_GREEDY if e.policy == 'greedy' else ops.POLICY_RANDOM for e in (self.proc_black, self.proc_white)]
+        po = ops.playout(n_games, seed=self.seed, gid0=self.next_gid, device=self.device, policy=pol[0],
+                         policy_white=pol[1], random_plies=self.random_plies, n_rand_black=self.n_rand_black,
+                         n_rand_white=self.n_rand_white, weights=self._weights[0], weights_white=self._weights[1],
+                         t_max=t_max, trajectory=trajectory, out=out)
         self.next_gid += int(n_games)
         return po
 

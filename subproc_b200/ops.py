@@ -207,7 +207,7 @@ class Playout:
 
 def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn0=None, policy=POLICY_RANDOM,
             random_plies=0, n_rand_black=0, n_rand_white=0, weights=None, t_max=T_MAX_DEFAULT, trajectory=True,
-            out=None):
+            out=None, policy_white=None, weights_white=None):
     """GameRunner.play_a_game (game_runner.py:165-201) for n_games games in ONE kernel launch.
 
     Game g draws from the counter-based stream (seed, gid0 + g): sharding games over launches or
@@ -230,6 +230,8 @@ def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn
     a.turn0 = _opt(turn0, torch.uint8, n, "turn0")
     a.policy, a.random_plies, a.n_rand_black, a.n_rand_white = policy, random_plies, n_rand_black, n_rand_white
     a.weights = _opt(weights, torch.float32, 40, "weights")
+    a.policy_white = -1 if policy_white is None else policy_white      # White's engine (None = same as Black's)
+    a.weights_white = _opt(weights_white, torch.float32, 40, "weights_white")
     a.t_max, a.stride = out.t_max, n
     a.traj_black = _opt(out.black, torch.int64, (out.t_max + 1) * n, "traj_black")
     a.traj_white = _opt(out.white, torch.int64, (out.t_max + 1) * n, "traj_white")

@@ -63,5 +63,19 @@ def test_game_runner_batches_and_winners(oracle):
     win = gr.winners(po1).cpu().numpy()
     cnt = oracle.counts(ref['final_black'][:300], ref['final_white'][:300])
     assert np.array_equal(win, np.sign(cnt[:, 0] - cnt[:, 1]).astype(np.int8))
+    # different engines per colour, like proc_black / proc_white (game_runner.py:107-123)
+    other = np.array([[3, 80, 40, -20, 5, 5, 1, 1, 2, 0], [10, 60, 30, -10, 4, 6, 2, 2, 1, 0],
+                      [20, 50, 20, -5, 3, 7, 3, 3, 3, 0], [64, 10, 10, 10, 10, 10, 10, 10, 10, 0]], dtype=np.float64)
+    for black, white, kw in (
+            ('random', Engine('greedy', oracle.DEFAULT_WEIGHTS), dict(policy=0, policy_white=1)),
+            (Engine('greedy', other, random_plies=3), 'random', dict(policy=1, policy_white=0, weights=other, random_plies=3)),
+            (Engine('greedy', oracle.DEFAULT_WEIGHTS, random_plies=2), Engine('greedy', other, random_plies=2),
+             dict(policy=1, policy_white=1, weights_white=other, random_plies=2))):
+        gr = GameRunner(black, white, None, False, 1, 2, device=DEV, seed=22)
+        po = gr.play_games(400)
+        ref = oracle.playout(22, 0, 400, n_rand_black=1, n_rand_white=2, **kw)
+        assert np.array_equal(po.nplies.cpu().numpy(), ref['nplies'])
+        assert np.array_equal(host_bits(po.final_black), ref['final_black'])
+        assert np.array_equal(host_bits(po.final_white), ref['final_white'])
     with pytest.raises(ValueError):
-        GameRunner('random', Engine('greedy', oracle.DEFAULT_WEIGHTS), None, False, 0, 0, device=DEV)
+        GameRunner(Engine('greedy', other, random_plies=1), Engine('greedy', other, random_plies=2), None, False, 0, 0, device=DEV)

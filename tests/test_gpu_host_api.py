@@ -56,7 +56,7 @@ def test_playout_host_small_with_host_trajectory(ctx, oracle):
     tm = np.zeros((t_max, n), np.uint8)
     npl, fb, fw = np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
     wts = oracle.DEFAULT_WEIGHTS.astype(np.float32)
-    assert L.othello_playout_host(ctx, 7, 1000, n, P(b0), P(w0), P(turn0), 1, 4, 2, 3, P(wts), t_max,
+    assert L.othello_playout_host(ctx, 7, 1000, n, P(b0), P(w0), P(turn0), 1, 4, 2, 3, P(wts), -1, None, t_max,
                                   P(tb), P(tw), P(tm), P(npl), P(fb), P(fw)) == 0
     ref = oracle.playout(7, 1000, n, black0=b0, white0=w0, turn0=turn0, policy=1, random_plies=4, n_rand_black=2,
                          n_rand_white=3, t_max=t_max)
@@ -73,7 +73,7 @@ def test_playout_host_chunked_pipeline_equals_one_launch(ctx):
     L = _lib.lib()
     n = 300000 + 17
     npl, fb, fw = np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-    assert L.othello_playout_host(ctx, 3, 55, n, None, None, None, 0, 0, 0, 0, None, 120, None, None, None,
+    assert L.othello_playout_host(ctx, 3, 55, n, None, None, None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
                                   P(npl), P(fb), P(fw)) == 0
     po = ops.playout(n, seed=3, gid0=55, device=DEV, trajectory=False)
     assert np.array_equal(npl, po.nplies.cpu().numpy())

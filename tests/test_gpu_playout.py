@@ -29,9 +29,11 @@ def test_golden_games_replayed_by_the_kernel(golden_games):
         w = ops.weights_tensor(np.array(
             [[100, 99, -1, -1, -1, -1, 3, 8, 20], [75, 99, 2, -5, 7, 6, 4, 5, 5],
              [25, 99, 2, -5, -7, -6, 4, 5, 5], [1, 100, 50, 30, 30, 30, 30, 30, 30]]), DEV)
+        ww = ops.weights_tensor(np.array(g['rows_white']), DEV) if 'rows_white' in g else None
         po = ops.playout(1, seed=g['seed'], gid0=g['gid'], device=DEV, policy=g['policy'],
                          random_plies=g['random_plies'], n_rand_black=g['n_rand_black'],
-                         n_rand_white=g['n_rand_white'], weights=w)
+                         n_rand_white=g['n_rand_white'], weights=w, policy_white=g.get('policy_white'),
+                         weights_white=ww)
         n = len(g['plies'])
         assert int(po.nplies.cpu()[0]) == n
         assert po.move[:n, 0].cpu().tolist() == [p['move'] for p in g['plies']]

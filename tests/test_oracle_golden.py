@@ -87,8 +87,12 @@ def test_games_every_ply(golden_games, oracle):
 def test_playout_loop_reproduces_reference_games(golden_games, oracle):
     """The oracle's game loop (go_for substitution, engines, RNG) replays the reference-driven games."""
     for g in golden_games:
+        ww = None
+        if 'rows_white' in g:
+            ww = np.concatenate([np.array(g['rows_white'], dtype=np.float64), np.zeros((4, 1))], axis=1)
         r = oracle.playout(g['seed'], g['gid'], 1, policy=g['policy'], random_plies=g['random_plies'],
-                           n_rand_black=g['n_rand_black'], n_rand_white=g['n_rand_white'])
+                           n_rand_black=g['n_rand_black'], n_rand_white=g['n_rand_white'],
+                           policy_white=g.get('policy_white'), weights_white=ww)
         n = len(g['plies'])
         assert int(r['nplies'][0]) == n
         assert r['move'][:n, 0].tolist() == [p['move'] for p in g['plies']]
