@@ -125,7 +125,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     # each step = a bounded sample of the workload; whole run stays within a few minutes
-    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    per_step = args.cpu_seconds if args.cpu_seconds else max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_baseline(budget_s=min(per_step, 3.0))
     total_plies = total_games = 0.0
@@ -244,7 +244,8 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the hot path is sm_100a kernels, there is no CPU fallback")
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(budget_s=args.cpu_seconds, full_path_s=args.cpu_seconds / 2)   # before CUDA is initialised (fork-safe)
+        secs = args.cpu_seconds if args.cpu_seconds else 12.0
+        cb, _ = cpu_baseline(budget_s=secs, full_path_s=secs / 2)          # before CUDA is initialised (fork-safe)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -384,7 +385,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU per step")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="seconds of host-core time per CPU sample (default: 12 for the cpu_baseline leg, "
+                         "90 / (steps + warmup) clamped to [2, 20] per step of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
