@@ -14,10 +14,6 @@ namespace ob {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-// files b..g: a disc that a horizontal/diagonal flood may pass THROUGH (a run can never
-// continue across the a/h edge, hands_for_direc stops at is_within_board, board.py:131-137)
-__device__ constexpr u64 kInner = 0x7E7E7E7E7E7E7E7Eull;
-
 // square-class masks a..h (parameter_progress_position_moves_learn.py:9-16)
 __device__ constexpr u64 kClassMask[8] = {
     0x8100000000000081ull, 0x4281000000008142ull, 0x0042000000004200ull, 0x2400810000810024ull,

@@ -1,10 +1,11 @@
-// fastboard.cuh -- the tuned rules primitives used inside the long-running kernels (playout,
-// perft, learner): same results as bitboard.cuh, ~40 % fewer ALU-pipe instructions per ply.
+// fastboard.cuh -- the rules primitives every kernel uses: Board.puttables (board.py:46-52) and
+// Board.put (board.py:161-174) on a pair of 64-bit bitboards held in registers.
 //
-// Why a second formulation: ncu shows the playout kernel is bound by the INT32 ALU pipe
-// (sm__inst_executed_pipe_alu 96 %, profiles/playout_r01_ncu_summary.txt) while the FMA pipe
-// (IMAD) and the XU pipe (BREV/POPC) idle.  On B200 a 64-bit RIGHT shift costs two ALU
-// instructions, a LEFT shift one ALU + one IMAD.SHL; BREV runs on the XU pipe.  So:
+// The formulation is shaped by what ncu showed on the first, textbook version (8-direction
+// Kogge-Stone floods in both shift directions): the playout kernel was bound by the INT32 ALU pipe
+// (sm__inst_executed_pipe_alu 96 %, profiles/playout_r01_ncu_summary.txt) while the FMA pipe (IMAD)
+// and the XU pipe (BREV/POPC) idled.  On B200 a 64-bit RIGHT shift costs two ALU instructions, a
+// LEFT shift one ALU + one IMAD.SHL; BREV runs on the XU pipe.  So:
 //
 //   * every flood runs to the LEFT: the four "down" directions are evaluated as "up" directions
 //     on the bit-reversed board (BREV64 = 2 XU instructions), results reversed back once;

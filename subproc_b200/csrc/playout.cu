@@ -1,7 +1,7 @@
 // playout.cu -- GameRunner.play_a_game (game_runner.py:165-201) for millions of games at once.
 //
 // One thread owns one game from the first ply to the last: the position lives in four 32-bit
-// registers pairs (own/opp bitboards), a ply is ~500 integer instructions and touches memory
+// registers (own/opp bitboards), a ply is ~385 integer instructions (fastboard.cuh) and touches memory
 // only to append the position and the move to the SoA trajectory [t][game] (a warp writes
 // 32 consecutive u64 = 256 B per array per ply).  The warp runs in lock step; games that end
 // early idle until the longest game of the warp is over.  Nothing is read from HBM after the
