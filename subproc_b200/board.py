@@ -65,10 +65,17 @@ class Board(object):
         return (self._black, self._white) if piece == Black else (self._white, self._black)
 
     def _legal_mask(self, piece):
-        ops, dev = self._ops()
-        own, opp = self._pair(piece)
-        out = ops.legal(ops.bits_tensor([own], dev), ops.bits_tensor([opp], dev))
-        return int(ops.bits_numpy(out)[0])
+        """legal moves of ``piece``: one launch answers both colours (a batch of two) and is remembered
+        until the position changes -- play_a_turn asks puttables / is_game_over for the same position
+        several times (game_runner.py:137,162; game_recorder.py:112)."""
+        key = (self._black, self._white)
+        if getattr(self, '_legal_key', None) != key:
+            ops, dev = self._ops()
+            out = ops.legal(ops.bits_tensor([self._black, self._white], dev),
+                            ops.bits_tensor([self._white, self._black], dev))
+            m = ops.bits_numpy(out)
+            self._legal_key, self._legal_both = key, (int(m[0]), int(m[1]))
+        return self._legal_both[0] if piece == Black else self._legal_both[1]
 
     # ---- the 8x8 list view -------------------------------------------------------------
     @property
