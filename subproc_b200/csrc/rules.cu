@@ -113,19 +113,27 @@ __global__ void __launch_bounds__(kThreads) mask_count_kernel(const u64 *__restr
     out[i] = __popcll(discs & mask[i]);
 }
 
-// counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17)
+// counts(a_book, side) (parameter_progress_position_moves_learn.py:5-17).  The [n][10] result is
+// staged through shared memory so that the CTA writes its 10 KB with unit-stride stores (a thread
+// writing its own 40-byte record would touch 32 sectors per store instruction).
 __global__ void __launch_bounds__(kThreads) features_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
                                                             const uint8_t *__restrict__ side, int32_t *__restrict__ out,
                                                             int64_t n)
 {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    const u64 b = black[i], w = white[i];
-    const bool is_black = side[i] == OTHELLO_BLACK;
-    int f[10];
-    features10(is_black ? b : w, is_black ? w : b, f);
+    __shared__ int32_t tile[kThreads * OTHELLO_FEATURES];
+    const int64_t base = (int64_t)blockIdx.x * kThreads;
+    const int64_t i = base + threadIdx.x;
+    if (i < n) {
+        const u64 b = black[i], w = white[i];
+        const bool is_black = side[i] == OTHELLO_BLACK;
+        int f[10];
+        features10(is_black ? b : w, is_black ? w : b, f);
 #pragma unroll
-    for (int k = 0; k < 10; k++) out[10 * i + k] = f[k];
+        for (int k = 0; k < 10; k++) tile[threadIdx.x * OTHELLO_FEATURES + k] = f[k];
+    }
+    __syncthreads();
+    const int64_t rows = (n - base < kThreads) ? n - base : kThreads;
+    for (int j = threadIdx.x; j < rows * OTHELLO_FEATURES; j += kThreads) out[base * OTHELLO_FEATURES + j] = tile[j];
 }
 
 // linear phase-weighted evaluation; the 160-byte weight table is staged in shared memory
