@@ -289,6 +289,31 @@ def run_b200_arm(args):
     positions = sum(int(t.sum(dtype=torch.int64).item()) for t in nplies_steps)
     games = K * G
 
+    # ---- the batch API on explicit positions: othello_step (put_s + game-over check) on synthetic
+    # random-opening positions = the positions of this launch after 10 random plies, their next move
+    t_open = 10
+    sb, sw = po.black[t_open].clone(), po.white[t_open].clone()
+    mv = po.move[t_open].contiguous()
+    wb, ww = torch.empty_like(sb), torch.empty_like(sw)
+    turn = torch.empty(G, dtype=torch.uint8, device=dev)
+    nturn = torch.empty(G, dtype=torch.int32, device=dev)
+    fl, rt, fg = torch.empty_like(sb), torch.empty(G, dtype=torch.int32, device=dev), torch.empty(G, dtype=torch.uint8, device=dev)
+    step_times = []
+    for i in range(3 + 5):
+        wb.copy_(sb); ww.copy_(sw); turn.fill_(ops.BLACK); nturn.fill_(t_open)      # restore (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.step(wb, ww, turn, nturn, mv, fl, rt, fg)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            step_times.append(e0.elapsed_time(e1))
+    step_live = int((rt > 0).sum().item())
+    step_info = {"positions_per_s": G / (min(step_times) * 1e-3), "kernel_ms": min(step_times), "positions": G,
+                 "legal_moves_applied": step_live,
+                 "what": "othello_step (put_s + pass / game-over flags) on the positions after %d random plies; "
+                         "50 B of HBM traffic per position" % t_open}
+
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------
     L = _lib.lib()
     ctx = ctypes.c_void_p()
@@ -367,6 +392,7 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": d2h, "games_per_s": G * K * n_gpus / (e2e_ms * 1e-3),
                     "api": "othello_playout_host (C ABI, pinned host buffers; trajectories stay in HBM)"},
             "gpu_launches": K,
+            "step_kernel": step_info,
             "clocks": clocks,
         }
         if cb is not None:
