@@ -39,6 +39,16 @@ __device__ __forceinline__ u32 rng_draw(u32 key, u32 ply, u32 stream)
 }
 __device__ __forceinline__ u32 rng_below(u32 r, u32 n) { return __umulhi(r, n); }
 
+// rng_draw with its three right shifts issued as IMAD.HI (h >> k == umulhi(h, 2^(32-k))) on the FMA
+// pipe; `one` is obf::kOpaqueOne so that ptxas cannot turn the multiplies back into ALU shifts
+__device__ __forceinline__ u32 rng_draw_fma(u32 key, u32 ply, u32 stream, u32 one)
+{
+    const u32 c16 = one << 16, c19 = one << 19;
+    u32 h = key + ply * 0x9E3779B9u + stream * 0x632BE5ABu;
+    h ^= __umulhi(h, c16); h *= 0x85EBCA6Bu; h ^= __umulhi(h, c19); h *= 0xC2B2AE35u; h ^= __umulhi(h, c16);
+    return h;
+}
+
 // ---- features / evaluation -------------------------------------------------------------------
 // phase row of a disc count: shards (0,16),(17,32),(33,48),(49,64) inclusive
 // (progress_position_moves_learn.py:75,112-113)

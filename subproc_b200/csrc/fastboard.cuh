@@ -225,8 +225,9 @@ template <typename RayTable>
 OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTable &rays)
 {
     const int sr = 63 - s;
-    const u64 x = 1ull << s, xr = 1ull << sr;
+    const u64 x = 1ull << s;
 #if defined(__CUDA_ARCH__)
+    const u64 xr = rev64(x);                   // two BREVs on the XU pipe instead of two more ALU shifts
     const u32 one = kOpaqueOne;
     u32 f_lo = 0, f_hi = 0, r_lo = 0, r_hi = 0;
 #pragma unroll
@@ -236,6 +237,7 @@ OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTab
     }
     return pack(f_lo, f_hi) | rev64(pack(r_lo, r_hi));
 #else
+    const u64 xr = 1ull << sr;
     u64 f = 0, fr = 0;
     for (int d = 0; d < kRayDirs; d++) {
         f |= ray_flips(x, rays(d, s), own, opp);

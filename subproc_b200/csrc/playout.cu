@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_pla
             if (obf::legal_moves(opp, own, opp_r, own_r) == 0) break;   // is_game_over (board.py:57-58)
         } else {
             const int n = __popcll(legal);
-            const u32 r1 = rng_draw(key, (u32)t, 1u);
+            const u32 r1 = rng_draw_fma(key, (u32)t, 1u, obf::kOpaqueOne);
             // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
             // random one; behind a random engine both draw the same k-th move from stream 1, so the
             // budgets n_rand_* do not change any game played by this kernel.
