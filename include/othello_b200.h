@@ -157,6 +157,15 @@ int othello_learn_accumulate(const uint64_t *traj_black, const uint64_t *traj_wh
                              int64_t n_games, int64_t stride, int32_t t_max, const double *decay /* [t_max+1] */,
                              double *stats, void *stream);
 
+/* fit_parameter for the four shards ON the device (progress_position_moves_learn.py:160-184, minus
+ * its sampling): OLS with intercept from stats[4][112] (minimum-norm when a shard is rank deficient),
+ * `coef * 127 / max|coef|`, int() truncation.  weights[4][10] receives the new float table the playout
+ * kernels read (intercept column 0), params[36] the stored integers ('A'.. order), fits[4][16] =
+ * coef[9], intercept, rmse, r2, n, 0, 0, 0.  A shard without samples keeps its row of prev_weights.
+ * All pointers DEVICE; weights may alias prev_weights. */
+int othello_learn_solve(const double *stats, const float *prev_weights, float *weights, int32_t *params,
+                        double *fits, void *stream);
+
 /* ---- the reference's value table, exactly ------------------------------------------------------ */
 
 /* __update_state_for_a_book (progress_position_moves_learn.py:37-48): one (key, new_value) record per

@@ -53,6 +53,7 @@ SIGNATURES = {
     "othello_perft": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, i64,
                                      u64p, vp]),
     "othello_learn_accumulate": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp]),
+    "othello_learn_solve": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "othello_value_records": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
     "othello_value_smooth": (ctypes.c_int, [vp, vp, vp, ctypes.c_double, vp, i64, vp]),
     "othello_unpack_keys": (ctypes.c_int, [vp, vp, i64, vp]),

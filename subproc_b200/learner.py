@@ -191,6 +191,35 @@ class ProgressPositionMovesLearn(object):
             self.last_processed_id = book_id
         return rows
 
+    def self_play_iterations_on_device(self, n_iterations, games_per_rank, seed=0, first_iteration=0, random_plies=10,
+                                       device=None, rank=0, world=1, t_max=120):
+        """config 5 without host round trips: every iteration is playout -> statistics -> all-reduce ->
+        othello_learn_solve -> the next playout reads the new table straight from device memory.  The
+        host only enqueues; parameters are copied back once at the end.  Same arithmetic as
+        ``self_play_iteration`` (the integer parameters may differ by one where a scaled coefficient
+        sits on an integer boundary: two eigen-solvers, last-ulp differences)."""
+        import torch
+        from . import ops
+        dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        w = torch.from_numpy(self.weights_table()).to(dev)
+        stats = torch.zeros((4, 112), dtype=torch.float64, device=dev)
+        po = params = fits = None
+        for it in range(first_iteration, first_iteration + n_iterations):
+            gid0 = (it * world + rank) * games_per_rank
+            po = ops.playout(games_per_rank, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
+                             random_plies=random_plies, weights=w, t_max=t_max, out=po)
+            stats.zero_()
+            ops.learn_accumulate(po, stats=stats, lam=self.l)
+            allreduce_stats(stats)
+            w, params, fits = ops.learn_solve(stats, w, weights_out=w)
+        self.params = [int(v) for v in params.cpu().tolist()]
+        f = fits.cpu().numpy()
+        self.last_fits = [dict(coef=f[s, :9].copy(), intercept=float(f[s, 9]), rmse=float(f[s, 10]), r2=float(f[s, 11]),
+                               n=int(f[s, 12])) for s in range(4)]
+        self.last_stats = stats
+        self.last_processed_id = ((first_iteration + n_iterations - 1) * world + rank + 1) * games_per_rank - 1
+        return po
+
     # ---- the reference's book-driven entry point ---------------------------------------------
     def learn_and_update_batch(self, books, device=None, sample=50000, seed=0):
         """LearnBasePlus.learn_and_update_batch (progress_position_moves_learn.py:88-101) on the

@@ -288,6 +288,21 @@ def learn_accumulate(po, stats=None, lam=0.90):
     return stats
 
 
+def learn_solve(stats, prev_weights, weights_out=None):
+    """The four per-phase fits on the device (no host round trip): returns (weights float32 [4][10],
+    params int32 [36], fits float64 [4][16] = coef[9], intercept, rmse, r2, n, 0, 0, 0)."""
+    dev = stats.device
+    weights_out = torch.empty((4, 10), dtype=torch.float32, device=dev) if weights_out is None else weights_out
+    params = torch.empty(36, dtype=torch.int32, device=dev)
+    fits = torch.empty((4, 16), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().othello_learn_solve(
+            _req(stats, torch.float64, 448, "stats"), _req(prev_weights, torch.float32, 40, "prev_weights"),
+            _req(weights_out, torch.float32, 40, "weights_out"), _req(params, torch.int32, 36, "params"),
+            _req(fits, torch.float64, 64, "fits"), _stream(stats)), "othello_learn_solve")
+    return weights_out, params, fits
+
+
 def int32_peak(device=None, iters=4096, blocks_per_sm=8, threads=256, repeats=5, dual=False):
     """Measured INT32 throughput (lane-ops/s) of this GPU: the integer roofline denominator.
 

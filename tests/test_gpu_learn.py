@@ -52,3 +52,42 @@ def test_learn_statistics_are_additive_over_shards_of_games():
         ops.learn_accumulate(ops.playout(1024, seed=8, gid0=1024 * k, device=DEV), stats=parts)
     assert torch.equal(whole[:, :100], parts[:, :100])
     assert torch.allclose(whole, parts, rtol=1e-9, atol=1e-9)
+
+
+def test_device_solve_matches_host_solve():
+    """othello_learn_solve (Jacobi on the device) vs learner.solve_shard (numpy eigh on the host) on real
+    statistics, incl. an empty shard and a shard whose corner classes are never occupied"""
+    from subproc_b200 import learner, parameter
+    w0 = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(DEV)
+    for n, t_max in ((20000, 120), (3000, 30)):                       # t_max = 30: the last phase shard stays empty
+        po = ops.playout(n, seed=14, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, random_plies=8, weights=w0, t_max=t_max)
+        if t_max < 120:
+            po.nplies.clamp_(max=t_max)                               # treat the truncated prefix as whole games
+        stats = ops.learn_accumulate(po)
+        w, params, fits = ops.learn_solve(stats, w0)
+        host = learner.fit_from_stats(stats)
+        f = fits.cpu().numpy()
+        for s in range(4):
+            if host[s]['n'] == 0:
+                assert torch.equal(w[s], w0[s]) and f[s, 12] == 0
+                continue
+            assert f[s, 12] == host[s]['n']
+            assert np.allclose(f[s, :9], host[s]['coef'], rtol=1e-8, atol=1e-10)
+            assert abs(f[s, 9] - host[s]['intercept']) <= 1e-8 * max(1.0, abs(host[s]['intercept']))
+            assert abs(f[s, 10] - host[s]['rmse']) <= 1e-8 * host[s]['rmse'] and abs(f[s, 11] - host[s]['r2']) < 1e-8
+            want = learner.stored_parameters([learner.scale_param(host[s]['coef'])])
+            got = params[9 * s:9 * s + 9].cpu().tolist()
+            assert max(abs(a - b) for a, b in zip(got, want)) <= 1 and max(abs(v) for v in got) in (126, 127)
+            assert w[s, :9].cpu().tolist() == [float(v) for v in got] and float(w[s, 9]) == 0.0
+
+
+def test_iterations_on_device_track_the_host_loop():
+    from subproc_b200 import learner
+    A, B = learner.ProgressPositionMovesLearn(), learner.ProgressPositionMovesLearn()
+    A.configure({}); B.configure({})
+    A.self_play_iteration(8192, seed=5, iteration=0, device=DEV)
+    B.self_play_iterations_on_device(1, 8192, seed=5, device=DEV)
+    assert max(abs(a - b) for a, b in zip(A.read_parameters(), B.read_parameters())) <= 1
+    assert [f['n'] for f in A.last_fits] == [f['n'] for f in B.last_fits]
+    B.self_play_iterations_on_device(3, 8192, seed=5, first_iteration=1, device=DEV)
+    assert all(-127 <= v <= 127 for v in B.read_parameters()[1:]) and B.last_processed() == 4 * 8192 - 1

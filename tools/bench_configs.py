@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--random-plies", type=int, default=10)
+    ap.add_argument("--device-solve", action="store_true", help="learner: refit on the device, no host round trip")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -79,6 +80,32 @@ def main():
         return (e0, e1)
 
     nplies_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    if args.workload == "learner" and args.device_solve:
+        # the whole loop is enqueued without waiting for the host: K iterations in one call
+        L.self_play_iterations_on_device(W, G, seed=2, first_iteration=0, random_plies=args.random_plies, device=dev,
+                                         rank=rank, world=world)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        L.self_play_iterations_on_device(K, G, seed=2, first_iteration=W, random_plies=args.random_plies, device=dev,
+                                         rank=rank, world=world)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"workload": "config5_parallel_learner_device_solve", "n_gpus": world,
+                              "games_per_gpu_per_step": G, "steps": K, "warmup": W, "ms_per_step": float(t[0]) / K,
+                              "games_per_s": K * G * world / (float(t[0]) * 1e-3),
+                              "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / K,
+                              "parameters": list(L.read_parameters())}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     for i in range(W):
         step(i)
         nplies_sum += po.nplies.sum(dtype=torch.int64)     # also warms torch's lazily loaded reduce kernel
