@@ -154,6 +154,14 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const u64 *__restrict__ 
 // Board.serialize_board (board.py:223-243): 64 characters per position, row-major, 'O' = Black,
 // 'X' = White, '-' = empty.  One thread writes one rank (8 characters = one 8-byte store), so a warp
 // writes 256 contiguous bytes: an HBM-bound codec (16 B read, 64 B written per position).
+// The 8 bits of a rank are spread to 8 bytes with multiplies (SWAR, mostly FMA pipe): per nibble
+// (v * 0x01010101) & 0x08040201 leaves bit k alone in byte k; +0x7F.. >> 7 turns it into 0 / 1.
+__device__ __forceinline__ u32 spread4(u32 nibble)          // 4 bits -> 4 bytes of 0 / 1
+{
+    const u32 t = (nibble * 0x01010101u) & 0x08040201u;
+    return ((t + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+}
+
 __global__ void __launch_bounds__(kThreads) serialize_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
                                                              u64 *__restrict__ out /* [n][8] */, int64_t n)
 {
@@ -161,33 +169,39 @@ __global__ void __launch_bounds__(kThreads) serialize_kernel(const u64 *__restri
     if (i >= n * 8) return;
     const int64_t pos = i >> 3;
     const int rank = (int)(i & 7);
-    const unsigned b = (unsigned)(black[pos] >> (8 * rank)) & 0xFFu, w = (unsigned)(white[pos] >> (8 * rank)) & 0xFFu;
-    u64 chars = 0;
-#pragma unroll
-    for (int x = 0; x < 8; x++) {
-        const unsigned c = ((b >> x) & 1u) ? 'O' : (((w >> x) & 1u) ? 'X' : '-');
-        chars |= (u64)c << (8 * x);
-    }
-    out[i] = chars;
+    const unsigned b = (unsigned)(black[pos] >> (8 * rank)) & 0xFFu, w = (unsigned)(white[pos] >> (8 * rank)) & 0xFFu & ~b;
+    // '-' = 0x2D, 'O' = 0x2D + 0x22, 'X' = 0x2D + 0x2B: no byte overflows, so plain multiplies and adds
+    const u32 lo = 0x2D2D2D2Du + spread4(b & 0xFu) * 0x22u + spread4(w & 0xFu) * 0x2Bu;
+    const u32 hi = 0x2D2D2D2Du + spread4(b >> 4) * 0x22u + spread4(w >> 4) * 0x2Bu;
+    out[i] = ((u64)hi << 32) | lo;
 }
 
 // Board.deserialize (board.py:253-262) of the 64-character board string; any character other than
 // 'O' / 'X' is an empty square (turn_from_string, board.py:245-251).  One thread per position reads
-// its 64 bytes as eight 8-byte words.
+// its 64 bytes as eight 8-byte words; per word the bytes equal to a character are found with the
+// exact SWAR zero-byte test and their flags gathered into 8 bits with one multiply.
+__device__ __forceinline__ u32 match4(u32 chars, u32 pattern)      // 4 bytes -> 4 bits (byte k == pattern byte)
+{
+    const u32 t = chars ^ pattern;
+    const u32 z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;      // bit 7 of byte k set iff byte k == 0
+    return (((z >> 7) * 0x01020408u) >> 24) & 0xFu;                           // gather the four flags: byte k -> bit k
+}
+
 __global__ void __launch_bounds__(kThreads) deserialize_kernel(const u64 *__restrict__ in /* [n][8] */,
                                                                u64 *__restrict__ black, u64 *__restrict__ white, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + i * 8);
     u64 b = 0, w = 0;
 #pragma unroll
-    for (int rank = 0; rank < 8; rank++) {
-        const u64 chars = in[i * 8 + rank];
+    for (int q = 0; q < 4; q++) {                             // 16 bytes = two ranks per load
+        const uint4 v = src[q];
+        const u32 word[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int x = 0; x < 8; x++) {
-            const unsigned c = (unsigned)(chars >> (8 * x)) & 0xFFu;
-            if (c == 'O') b |= 1ull << (8 * rank + x);
-            else if (c == 'X') w |= 1ull << (8 * rank + x);
+        for (int k = 0; k < 4; k++) {
+            b |= (u64)match4(word[k], 0x4F4F4F4Fu) << (16 * q + 4 * k);      // squares 16q + 4k .. + 3, 'O'
+            w |= (u64)match4(word[k], 0x58585858u) << (16 * q + 4 * k);      // 'X'
         }
     }
     black[i] = b; white[i] = w;

@@ -53,5 +53,18 @@ vt = value_table.ValueTable(device=dev)
 torch.cuda.synchronize(); t0 = time.perf_counter(); nrec = vt.update_from_playout(small); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 out.append(("value_table.update(65536 games)", nrec / dt, "records/s (wall, incl. sort)", None))
+# the HBM-bound codecs and batch rules at a size where launch latency no longer matters (2^24 positions)
+big = 1 << 24
+rep = big // n
+bb2, ww2 = b.repeat(rep), w.repeat(rep)
+t2 = torch.ones(big, dtype=torch.uint8, device=dev)
+ms = timed(lambda: ops.serialize_boards(bb2, ww2)); out.append(("othello_serialize_boards @2^24", big / ms * 1e3, "positions/s", 80 * big / ms / 1e6))
+chars = ops.serialize_boards(bb2, ww2)
+ms = timed(lambda: ops.deserialize_boards(chars)); out.append(("othello_deserialize_boards @2^24", big / ms * 1e3, "positions/s", 80 * big / ms / 1e6))
+del chars
+ms = timed(lambda: ops.legal(bb2, ww2)); out.append(("othello_legal @2^24", big / ms * 1e3, "positions/s", 24 * big / ms / 1e6))
+ms = timed(lambda: ops.features(bb2, ww2, t2)); out.append(("othello_features @2^24", big / ms * 1e3, "positions/s", 57 * big / ms / 1e6))
+ms = timed(lambda: ops.evaluate(bb2, ww2, t2, wts)); out.append(("othello_eval @2^24", big / ms * 1e3, "positions/s", 21 * big / ms / 1e6))
+ms = timed(lambda: ops.counts(bb2, ww2)); out.append(("othello_counts @2^24", big / ms * 1e3, "positions/s", 28 * big / ms / 1e6))
 for name, v, unit, gbs in out:
     print(json.dumps({"kernel": name, "value": v, "unit": unit, "hbm_GBps": gbs}))
