@@ -85,7 +85,7 @@ int othello_mask_count(const uint64_t *black, const uint64_t *white, const uint8
 
 /* Board.serialize_board / Board.deserialize (board.py:223-262): the 64-character row-major board
  * string of the recorder schema ('O' = Black, 'X' = White, '-' = empty; game_recorder.py:108-113).
- * chars: DEVICE char[n][64], 8-byte aligned.  Any other character deserialises to an empty square. */
+ * chars: DEVICE char[n][64], 16-byte aligned.  Any other character deserialises to an empty square. */
 int othello_serialize_boards(const uint64_t *black, const uint64_t *white, char *chars, int64_t n, void *stream);
 int othello_deserialize_boards(const char *chars, uint64_t *black, uint64_t *white, int64_t n, void *stream);
 

@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const u64 *__restrict__ 
 }
 
 // Board.serialize_board (board.py:223-243): 64 characters per position, row-major, 'O' = Black,
-// 'X' = White, '-' = empty.  One thread writes one rank (8 characters = one 8-byte store), so a warp
-// writes 256 contiguous bytes: an HBM-bound codec (16 B read, 64 B written per position).
+// 'X' = White, '-' = empty: an HBM-bound codec (16 B read, 64 B written per position).
 // The 8 bits of a rank are spread to 8 bytes with multiplies (SWAR, mostly FMA pipe): per nibble
 // (v * 0x01010101) & 0x08040201 leaves bit k alone in byte k; +0x7F.. >> 7 turns it into 0 / 1.
 __device__ __forceinline__ u32 spread4(u32 nibble)          // 4 bits -> 4 bytes of 0 / 1
@@ -162,18 +161,37 @@ __device__ __forceinline__ u32 spread4(u32 nibble)          // 4 bits -> 4 bytes
     return ((t + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
 }
 
+// One thread converts one position (16 u32 of characters); the warp's 2 KB go through shared memory so
+// that every store instruction writes 512 contiguous bytes (a thread storing its own 64-byte record
+// would touch 32 half-filled sectors per instruction).
 __global__ void __launch_bounds__(kThreads) serialize_kernel(const u64 *__restrict__ black, const u64 *__restrict__ white,
-                                                             u64 *__restrict__ out /* [n][8] */, int64_t n)
+                                                             uint4 *__restrict__ out /* [n][4] */, int64_t n)
 {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n * 8) return;
-    const int64_t pos = i >> 3;
-    const int rank = (int)(i & 7);
-    const unsigned b = (unsigned)(black[pos] >> (8 * rank)) & 0xFFu, w = (unsigned)(white[pos] >> (8 * rank)) & 0xFFu & ~b;
-    // '-' = 0x2D, 'O' = 0x2D + 0x22, 'X' = 0x2D + 0x2B: no byte overflows, so plain multiplies and adds
-    const u32 lo = 0x2D2D2D2Du + spread4(b & 0xFu) * 0x22u + spread4(w & 0xFu) * 0x2Bu;
-    const u32 hi = 0x2D2D2D2Du + spread4(b >> 4) * 0x22u + spread4(w >> 4) * 0x2Bu;
-    out[i] = ((u64)hi << 32) | lo;
+    __shared__ uint4 tile[kThreads / 32][32 * 4 + 4];          // per warp: 32 positions x 4 uint4 (+ padding)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = ((int64_t)blockIdx.x * kThreads + warp * 32);
+    const int64_t i = warp_base + lane;
+    if (i < n) {
+        const u64 b = black[i], w = white[i] & ~b;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                         // two ranks (16 characters) per uint4
+            u32 c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 nb = (u32)(b >> (16 * q + 4 * k)) & 0xFu, nw = (u32)(w >> (16 * q + 4 * k)) & 0xFu;
+                // '-' = 0x2D, 'O' = 0x2D + 0x22, 'X' = 0x2D + 0x2B: no byte overflows, plain multiplies and adds
+                c[k] = 0x2D2D2D2Du + spread4(nb) * 0x22u + spread4(nw) * 0x2Bu;
+            }
+            tile[warp][lane * 4 + q + (lane >> 3)] = make_uint4(c[0], c[1], c[2], c[3]);
+        }
+    }
+    __syncwarp();
+    const int64_t rows = n - warp_base;                         // positions of this warp that exist
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int j = r * 32 + lane;                            // uint4 index inside the warp's 2 KB
+        if ((j >> 2) < rows) out[warp_base * 4 + j] = tile[warp][j + ((j >> 2) >> 3)];
+    }
 }
 
 // Board.deserialize (board.py:253-262) of the 64-character board string; any character other than
@@ -213,16 +231,16 @@ extern "C" {
 
 int othello_serialize_boards(const uint64_t *black, const uint64_t *white, char *out, int64_t n, void *stream)
 {
-    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && out)) && ((uintptr_t)out & 7) == 0);
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && out)) && ((uintptr_t)out & 15) == 0);
     if (n == 0) return 0;
-    serialize_kernel<<<ob_blocks(n * 8, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black,
-                                                                                      (const u64 *)white, (u64 *)out, n);
+    serialize_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)black, (const u64 *)white,
+                                                                                  (uint4 *)out, n);
     return ob_launch_status();
 }
 
 int othello_deserialize_boards(const char *in, uint64_t *black, uint64_t *white, int64_t n, void *stream)
 {
-    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && in)) && ((uintptr_t)in & 7) == 0);
+    OB_CHECK_ARGS(n >= 0 && (n == 0 || (black && white && in)) && ((uintptr_t)in & 15) == 0);
     if (n == 0) return 0;
     deserialize_kernel<<<ob_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const u64 *)in, (u64 *)black,
                                                                                     (u64 *)white, n);
