@@ -104,8 +104,8 @@ extern "C" int othello_playout(const othello_playout_args *args, void *stream)
     OB_CHECK_ARGS(a.policy != OTHELLO_POLICY_GREEDY || a.weights != nullptr);
     OB_CHECK_ARGS(policy_white != OTHELLO_POLICY_GREEDY || a.weights != nullptr || a.weights_white != nullptr);
     OB_CHECK_ARGS(a.n_rand_black >= 0 && a.n_rand_white >= 0 && a.random_plies >= 0);
-    if (a.traj_black || a.traj_white || a.traj_move)
-        OB_CHECK_ARGS(a.traj_black && a.traj_white && a.traj_move && a.t_max >= 0 && a.stride >= a.n_games);
+    if (a.traj_black || a.traj_white || a.traj_move)       // (a capacity of 0 plies records only the start position)
+        OB_CHECK_ARGS(a.traj_black && a.traj_white && (a.traj_move || a.t_max == 0) && a.t_max >= 0 && a.stride >= a.n_games);
     const bool greedy = a.policy == OTHELLO_POLICY_GREEDY || policy_white == OTHELLO_POLICY_GREEDY;
     cudaStream_t s = (cudaStream_t)stream;
     if (greedy) return ob_launch_greedy(a, s);

@@ -235,7 +235,7 @@ def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn
     a.t_max, a.stride = out.t_max, n
     a.traj_black = _opt(out.black, torch.int64, (out.t_max + 1) * n, "traj_black")
     a.traj_white = _opt(out.white, torch.int64, (out.t_max + 1) * n, "traj_white")
-    a.traj_move = _opt(out.move, torch.uint8, out.t_max * n, "traj_move")
+    a.traj_move = _opt(out.move, torch.uint8, out.t_max * n, "traj_move") if out.t_max > 0 else None
     a.nplies = _req(out.nplies, torch.int32, n, "nplies")
     a.final_black = _req(out.final_black, torch.int64, n, "final_black")
     a.final_white = _req(out.final_white, torch.int64, n, "final_white")

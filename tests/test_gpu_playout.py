@@ -90,6 +90,20 @@ def test_truncated_trajectory_capacity(oracle):
     assert (po.nplies > 20).all()
 
 
+def test_zero_capacity_and_single_game(oracle):
+    po = ops.playout(5, seed=2, gid0=0, device=DEV, t_max=0)              # records the start position only
+    assert np.array_equal(po.nplies.cpu().numpy(), oracle.playout(2, 0, 5)['nplies'])
+    assert host_bits(po.black[0]).tolist() == [oracle.START_BLACK] * 5
+    one = ops.playout(1, seed=2, gid0=3, device=DEV)
+    assert int(one.nplies[0]) == int(po.nplies[3])
+    b0, w0, t0 = [0, 1, 2 ** 64 - 1, 1], [0, 2, 0, 4], [1, 2, 1, 1]           # empty, pass-then-move, full, dead
+    tiny = ops.playout(4, seed=1, gid0=0, device=DEV, black0=dev_bits(b0), white0=dev_bits(w0), turn0=dev_u8(t0))
+    ref = oracle.playout(1, 0, 4, black0=np.array(b0, np.uint64), white0=np.array(w0, np.uint64), turn0=np.array(t0, np.uint8))
+    assert tiny.nplies.cpu().tolist() == ref['nplies'].tolist() == [0, 2, 0, 0]
+    assert np.array_equal(host_bits(tiny.final_black), ref['final_black'])
+    assert np.array_equal(host_bits(tiny.final_white), ref['final_white'])
+
+
 def test_million_games_round_trip_properties():
     """BASELINE config 3 at full size: every recorded ply, replayed through the step kernel, must
     reproduce the next recorded position; finals are terminal; disc counts are consistent."""
