@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned ordered_bits(float v)
 }
 
 template <bool SUBST, bool TRAJ>
-__global__ void __launch_bounds__(kThreads) greedy_kernel(const othello_playout_args a)
+__global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playout_args a)
 {
     constexpr int kW = OTHELLO_PHASES * OTHELLO_WEIGHTS;
     __shared__ float w_s[2 * kW];                             // Black's table, then White's
