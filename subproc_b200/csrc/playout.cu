@@ -20,7 +20,52 @@ using namespace obp;
 namespace {
 
 // the random engine (uniform over puttables()); the greedy engine lives in greedy.cu
-template <bool TRAJ>
+struct Game {
+    u64 own, opp;
+    u64 *tb, *tw;
+    uint8_t *tm;
+    int t;
+};
+
+// One ply.  BLACK: 1 = Black moves, 0 = White moves (known at compile time when every game of the
+// launch starts with the same colour: Black and White then alternate strictly, passes included),
+// -1 = read `black_moves`.  Returns false when the game is over.
+template <bool TRAJ, int BLACK>
+__device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int t_max, int64_t stride, const Rays &rays)
+{
+    const bool bm = BLACK < 0 ? black_moves : (BLACK == 1);
+    if (TRAJ && g.t <= t_max) {
+        __stcs(g.tb, bm ? g.own : g.opp);
+        __stcs(g.tw, bm ? g.opp : g.own);
+        g.tb += stride; g.tw += stride;
+    }
+    const u64 own_r = obf::rev64(g.own), opp_r = obf::rev64(g.opp);
+    const u64 legal = obf::legal_moves(g.own, g.opp, own_r, opp_r);
+    int move = OTHELLO_PASS;
+    u64 f = 0, x = 0;
+    if (legal == 0) {
+        if (obf::legal_moves(g.opp, g.own, opp_r, own_r) == 0) return false;   // is_game_over (board.py:57-58)
+    } else {
+        const int n = __popcll(legal);
+        const u32 r1 = rng_draw_fma(key, (u32)g.t, 1u, obf::kOpaqueOne);
+        // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
+        // random one; behind a random engine both draw the same k-th move from stream 1, so the
+        // budgets n_rand_* do not change any game played by this kernel.
+        move = obf::kth_set_bit(legal, (int)rng_below(r1, (u32)n));
+        x = 1ull << move;
+        f = obf::flips_for(move, g.own, g.opp, own_r, opp_r, rays);
+    }
+    if (TRAJ && g.t < t_max) { __stcs(g.tm, (uint8_t)move); g.tm += stride; }
+    // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
+    const u64 moved = g.own | f | x;
+    g.own = g.opp & ~f;
+    g.opp = moved;
+    g.t++;
+    return true;
+}
+
+// UNIFORM: no per-game turn0 -- every game starts with Black, so the loop is unrolled over the two colours
+template <bool TRAJ, bool UNIFORM>
 // (128 threads x >= 10 CTAs per SM measured best on B200: 64/128/256 threads and 9..12 CTAs are within 2 %)
 __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
 {
@@ -28,63 +73,45 @@ __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_pla
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
-    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (g >= a.n_games) return;
+    const int64_t gi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (gi >= a.n_games) return;
 
-    const u64 b0 = a.black0 ? a.black0[g] : OTHELLO_START_BLACK;
-    const u64 w0 = a.white0 ? a.white0[g] : OTHELLO_START_WHITE;
-    bool black_moves = a.turn0 ? (a.turn0[g] == OTHELLO_BLACK) : true;
-    u64 own = black_moves ? b0 : w0, opp = black_moves ? w0 : b0;
-
-    const u32 key = rng_key(a.seed, a.gid0 + (u64)g);
-
-    u64 *tb = TRAJ ? (u64 *)a.traj_black + g : nullptr;
-    u64 *tw = TRAJ ? (u64 *)a.traj_white + g : nullptr;
-    uint8_t *tm = TRAJ ? a.traj_move + g : nullptr;
+    const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
+    const u64 w0 = a.white0 ? a.white0[gi] : OTHELLO_START_WHITE;
+    bool black_moves = UNIFORM ? true : (a.turn0[gi] == OTHELLO_BLACK);
+    Game g;
+    g.own = black_moves ? b0 : w0; g.opp = black_moves ? w0 : b0;
+    g.tb = TRAJ ? (u64 *)a.traj_black + gi : nullptr;
+    g.tw = TRAJ ? (u64 *)a.traj_white + gi : nullptr;
+    g.tm = TRAJ ? a.traj_move + gi : nullptr;
+    g.t = 0;
+    const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
     const int t_max = a.t_max;
     const int64_t stride = a.stride;
 
-    int t = 0;
-    for (;;) {
-        if (TRAJ && t <= t_max) {
-            __stcs(tb, black_moves ? own : opp);
-            __stcs(tw, black_moves ? opp : own);
-            tb += stride; tw += stride;
+    if (UNIFORM) {
+        for (;;) {
+            if (!play_ply<TRAJ, 1>(g, true, key, t_max, stride, rays)) { black_moves = true; break; }
+            if (!play_ply<TRAJ, 0>(g, false, key, t_max, stride, rays)) { black_moves = false; break; }
         }
-        const u64 own_r = obf::rev64(own), opp_r = obf::rev64(opp);
-        const u64 legal = obf::legal_moves(own, opp, own_r, opp_r);
-        int move = OTHELLO_PASS;
-        u64 f = 0, x = 0;
-        if (legal == 0) {
-            if (obf::legal_moves(opp, own, opp_r, own_r) == 0) break;   // is_game_over (board.py:57-58)
-        } else {
-            const int n = __popcll(legal);
-            const u32 r1 = rng_draw_fma(key, (u32)t, 1u, obf::kOpaqueOne);
-            // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
-            // random one; behind a random engine both draw the same k-th move from stream 1, so the
-            // budgets n_rand_* do not change any game played by this kernel.
-            move = obf::kth_set_bit(legal, (int)rng_below(r1, (u32)n));
-            x = 1ull << move;
-            f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
-        }
-        if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
-        // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
-        const u64 moved = own | f | x;
-        own = opp & ~f;
-        opp = moved;
-        black_moves = !black_moves;
-        t++;
+    } else {
+        while (play_ply<TRAJ, -1>(g, black_moves, key, t_max, stride, rays)) black_moves = !black_moves;
     }
-    a.nplies[g] = t;
-    a.final_black[g] = black_moves ? own : opp;
-    a.final_white[g] = black_moves ? opp : own;
+    a.nplies[gi] = g.t;
+    a.final_black[gi] = black_moves ? g.own : g.opp;
+    a.final_white[gi] = black_moves ? g.opp : g.own;
 }
 
 int launch(const othello_playout_args &a, cudaStream_t s)
 {
     const unsigned blocks = ob_blocks(a.n_games, kThreads);
-    if (a.traj_black) playout_kernel<true><<<blocks, kThreads, 0, s>>>(a);
-    else playout_kernel<false><<<blocks, kThreads, 0, s>>>(a);
+    if (a.traj_black) {
+        if (a.turn0) playout_kernel<true, false><<<blocks, kThreads, 0, s>>>(a);
+        else playout_kernel<true, true><<<blocks, kThreads, 0, s>>>(a);
+    } else {
+        if (a.turn0) playout_kernel<false, false><<<blocks, kThreads, 0, s>>>(a);
+        else playout_kernel<false, true><<<blocks, kThreads, 0, s>>>(a);
+    }
     return ob_launch_status();
 }
 
