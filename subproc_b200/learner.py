@@ -220,6 +220,31 @@ class ProgressPositionMovesLearn(object):
         self.last_processed_id = ((first_iteration + n_iterations - 1) * world + rank + 1) * games_per_rank - 1
         return po
 
+    # ---- checkpoint / resume ------------------------------------------------------------------
+    def save(self, path):
+        """Everything the reference keeps in Redis for this learner (progress_position_moves_learn.py:
+        188-224 and the value table :52): last processed book id, the stored parameters, the table."""
+        import torch
+        table = getattr(self, 'table', None)
+        torch.save({'name': self.name(), 'last_processed': self.last_processed_id, 'params': self.params,
+                    'a': self.a, 'l': self.l,
+                    'table_keys': None if table is None else table.keys.cpu(),
+                    'table_values': None if table is None else table.values.cpu()}, path)
+
+    def load(self, path, device=None):
+        import torch
+        from . import value_table
+        state = torch.load(path, map_location='cpu')
+        if state['name'] != self.name():
+            raise ValueError("checkpoint belongs to learner %r" % state['name'])
+        self.last_processed_id, self.params, self.a, self.l = state['last_processed'], state['params'], state['a'], state['l']
+        self.table = None
+        if state['table_keys'] is not None:
+            self.table = value_table.ValueTable(device=device, a=self.a, lam=self.l)
+            self.table.keys = state['table_keys'].to(self.table.device)
+            self.table.values = state['table_values'].to(self.table.device)
+        return self
+
     # ---- the reference's book-driven entry point ---------------------------------------------
     def learn_and_update_batch(self, books, device=None, sample=50000, seed=0):
         """LearnBasePlus.learn_and_update_batch (progress_position_moves_learn.py:88-101) on the

@@ -81,3 +81,18 @@ def test_book_driven_learn_and_update_batch_equals_trajectory_path(oracle):
     stats = L.store_batch_stats(po)
     c = po.final_counts().cpu().numpy()
     assert stats['min_disc_diff'] == int((c[:, 0] - c[:, 1]).min()) and len(stats['diffs']) == n
+
+
+def test_learner_checkpoint_round_trip(tmp_path):
+    """resume = the reference restarting on its Redis state: last_processed, parameters, value table"""
+    from subproc_b200 import books, learner
+    po = ops.playout(30, seed=35, gid0=0, device=DEV)
+    bks = [(i + 1, list(reversed(recs)), meta) for i, (recs, meta) in enumerate(books.books_from_playout(po))]
+    A = learner.ProgressPositionMovesLearn(); A.configure({})
+    A.learn_and_update_batch(bks[:20], device=DEV, sample=500)
+    A.save(str(tmp_path / "learner.pt"))
+    B = learner.ProgressPositionMovesLearn().load(str(tmp_path / "learner.pt"), device=DEV)
+    assert B.last_processed() == 20 and B.read_parameters() == A.read_parameters() and B.table.items() == A.table.items()
+    A.learn_and_update_batch(bks[20:], device=DEV, sample=500, seed=9)
+    B.learn_and_update_batch(bks[20:], device=DEV, sample=500, seed=9)
+    assert B.table.items() == A.table.items() and B.read_parameters() == A.read_parameters()
