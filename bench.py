@@ -154,6 +154,23 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# host-side placement of a rank
+# ------------------------------------------------------------------------------------------------
+def bind_rank_to_cores(local, world):
+    """Give every rank of a node its own contiguous share of the cores this process may run on, so the
+    submission threads of N ranks (and their pinned buffers, first-touched from those cores) do not
+    migrate over each other.  Returns what was done, for the JSON line."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return {"cores": "%d-%d" % (mine[0], mine[-1]), "n": len(mine), "of": len(cores)}
+    except (AttributeError, OSError) as e:           # pragma: no cover - platform without sched_setaffinity
+        return {"error": str(e)}
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
@@ -231,6 +248,120 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def config4_extra(dev, rank, world, G=1 << 19, reps=5, random_plies=10):
+    """BASELINE config 4 under the driver: greedy self-play with the default_value() rows
+    (parameter_progress_position_moves_learn.py:30-36), G games per GPU, first `random_plies` plies
+    uniform-random (N_RAND_HAND_UNTIL, game_runner.py:6), full trajectories.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from subproc_b200 import ops, parameter
+    w = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(dev)
+    pg = ops.playout(G, seed=2, gid0=rank * G, device=dev, policy=ops.POLICY_GREEDY, random_plies=random_plies, weights=w)
+    tot = torch.zeros(4, dtype=torch.int64, device=dev)
+    for i in range(2):
+        ops.playout(G, seed=2, gid0=(world * (1 + i) + rank) * G, device=dev, policy=ops.POLICY_GREEDY,
+                    random_plies=random_plies, weights=w, out=pg)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        ops.playout(G, seed=2, gid0=(world * (3 + i) + rank) * G, device=dev, policy=ops.POLICY_GREEDY,
+                    random_plies=random_plies, weights=w, out=pg, totals=tot)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # children evaluated by the last launch: sum of mobility over the plies the greedy engine searched
+    children = torch.zeros((), dtype=torch.int64, device=dev)
+    zero = torch.zeros(G, dtype=torch.int64, device=dev)
+    for t in range(random_plies, int(pg.nplies.max().item())):
+        own, opp = (pg.black[t], pg.white[t]) if t % 2 == 0 else (pg.white[t], pg.black[t])   # Black, White alternate strictly
+        n = ops.counts(ops.legal(own, opp), zero)[:, 0].to(torch.int64)
+        children += torch.where((pg.nplies > t) & (n > 1), n, torch.zeros_like(n)).sum()
+    v = torch.tensor([float(tot[0]), float(G * reps), float(children) * reps], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    sec = float(tmax[0]) * 1e-3
+    return {"workload": "config4_greedy_selfplay", "games_per_gpu": G, "random_plies": random_plies, "launches": reps,
+            "weights": "default_value() rows", "kernel_ms": float(tmax[0]) / reps,
+            "positions_per_s": float(v[0]) / sec, "games_per_s": float(v[1]) / sec,
+            "children_per_s": float(v[2]) / sec,
+            "children_note": "successor positions evaluated (flip + move generation + 9-term evaluation each); counted "
+                             "on the last launch and scaled by the number of launches",
+            "black_minus_white_mean": float(tot[1]) / float(G * reps)}
+
+
+def config5_extra(dev, rank, world, G=1 << 16, iters=10, warm=3, random_plies=10):
+    """BASELINE config 5 under the driver: per iteration greedy self-play with the current weights ->
+    exact integer statistics -> ONE all-reduce (NCCL) of 320 int64 -> four regressions on the device ->
+    the next self-play reads the new table.  Replaces the Redis `fitting:*` polling
+    (progress_position_moves_learn.py:112-158, parallel_learner_task.py:8-23).  Carries its own parity bits."""
+    import torch
+    import torch.distributed as dist
+    from subproc_b200 import ops, parameter, learner
+    w = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(dev)
+    acc = torch.zeros((4, learner.N_ACC), dtype=torch.int64, device=dev)
+    stats = torch.empty((4, 112), dtype=torch.float64, device=dev)
+    po = params = None
+    ar = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w_used = None
+    for it in range(warm + iters):
+        if it == warm:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0.record()
+        if it == warm + iters - 1:
+            w_used = w.clone()
+        po = ops.playout(G, seed=3, gid0=(it * world + rank) * G, device=dev, policy=ops.POLICY_GREEDY,
+                         random_plies=random_plies, weights=w, out=po)
+        acc.zero_()
+        ops.learn_accumulate(po, acc=acc)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        learner.allreduce_stats(acc)
+        a1.record()
+        if it >= warm:
+            ar.append((a0, a1))
+        ops.learn_stats(acc, out=stats)
+        w, params, _fits = ops.learn_solve(stats, w, weights_out=w)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / iters
+    ar_ms = sorted(a.elapsed_time(b) for a, b in ar)[len(ar) // 2]
+    # parity: (1) the all-reduced accumulators of the last iteration == rank 0 replaying the union of the ranks'
+    # game ids alone; (2) every rank ends with the same parameters
+    same_acc = True
+    if rank == 0:
+        it = warm + iters - 1
+        union = ops.playout(G * world, seed=3, gid0=it * world * G, device=dev, policy=ops.POLICY_GREEDY,
+                            random_plies=random_plies, weights=w_used)
+        same_acc = bool(torch.equal(ops.learn_accumulate(union), acc))
+        del union
+    same_params = True
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.empty_like(params) for _ in range(world)]
+        dist.all_gather(gathered, params)
+        same_params = all(bool(torch.equal(g, params)) for g in gathered)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"workload": "config5_parallel_learner", "games_per_gpu_per_iteration": G, "iterations": iters,
+            "iteration_ms": ms, "games_per_s": G * world / (ms * 1e-3), "allreduce_ms": ar_ms if world > 1 else None,
+            "allreduce_bytes": 4 * learner.N_ACC * 8, "nranks": world,
+            "launches_per_iteration": "greedy_kernel, learn_kernel, [ncclAllReduce], stats_kernel, solve_kernel",
+            "parity": {"allreduced_accumulators_equal_rank0_replay_of_all_game_ids": same_acc,
+                       "parameters_identical_on_all_ranks": same_params},
+            "parameters": [int(v) for v in params.cpu().tolist()],
+            "fit": "normal equations over every (position, side) sample of the iteration; the reference instead fits "
+                   "each shard on <= 50 000 keys sampled from its smoothed value table "
+                   "(progress_position_moves_learn.py:66-86,160-184) -- that path is subproc_b200.value_table"}
+
+
 def run_b200_arm(args):
     import ctypes
     import torch
@@ -246,6 +377,10 @@ def run_b200_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         secs = args.cpu_seconds if args.cpu_seconds else 12.0
         cb, _ = cpu_baseline(budget_s=secs, full_path_s=secs / 2)          # before CUDA is initialised (fork-safe)
+    # host side of a rank: its own cores, one intra-op thread (the only torch CPU work left is scalars)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    binding = bind_rank_to_cores(local, local_world) if local_world > 1 else None
+    torch.set_num_threads(1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -315,6 +450,11 @@ def run_b200_arm(args):
                          "50 B of HBM traffic per position" % t_open}
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------
+    # The call a user without torch makes: start positions in pinned host memory go
+    # in, per-game results (plies, final position) and the batch totals come back to pinned host
+    # memory, every step.  Two batches are kept in flight (othello_playout_host_async / othello_ctx_wait),
+    # so the PCIe copies of one step run under the kernels of its neighbours; the timed region still
+    # starts with nothing in flight and ends when the last result of step K is in host memory.
     L = _lib.lib()
     ctx = ctypes.c_void_p()
     _lib.check(L.othello_ctx_create(local, ctypes.byref(ctx)), "othello_ctx_create")
@@ -322,27 +462,56 @@ def run_b200_arm(args):
     h_b0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_BLACK))
     h_w0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_WHITE))
     h_t0 = pin(G, torch.uint8).fill_(ops.BLACK)
-    h_np, h_fb, h_fw = pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64)
+    h_out = [(pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64), pin(4, torch.int64)) for _ in range(2)]
     P = lambda t: ctypes.c_void_p(t.data_ptr())
+    e2e_gid = [gid_base + (W + K) * G]
 
-    def e2e_step(i):
-        _lib.check(L.othello_playout_host(ctx, 1, gid_base + (W + K + i) * G, G, P(h_b0), P(h_w0), P(h_t0),
-                                          ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX, None, None, None,
-                                          P(h_np), P(h_fb), P(h_fw)), "othello_playout_host")
-        return int(h_np.sum(dtype=torch.int64).item())
+    def e2e_run(steps):
+        """issue step i+1, then collect step i; returns the positions played (from the batch totals)"""
+        tickets = [0, 0]
+        played = 0
+        for i in range(steps + 1):
+            if i < steps:
+                o = h_out[i % 2]
+                tk = ctypes.c_int64()
+                _lib.check(L.othello_playout_host_async(
+                    ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), P(h_t0), ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX,
+                    None, None, None, P(o[0]), P(o[1]), P(o[2]), P(o[3]), ctypes.byref(tk)), "othello_playout_host_async")
+                e2e_gid[0] += G
+                tickets[i % 2] = tk.value
+            if i > 0:
+                _lib.check(L.othello_ctx_wait(ctx, tickets[(i - 1) % 2]), "othello_ctx_wait")
+                played += int(h_out[(i - 1) % 2][3][0])                  # the step's result, read on the host
+        return played
 
-    for i in range(max(1, min(W, 2))):
-        e2e_step(K + i)
+    e2e_run(max(3, min(W, 5)))
     barrier()
     t0 = time.perf_counter()
-    e2e_positions = 0
-    for i in range(K):
-        e2e_positions += e2e_step(i)
+    e2e_positions = e2e_run(K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # untimed check of the last batch: per-game results on the host agree with the device-side totals
+    last = h_out[(K - 1) % 2]
+    e2e_ok = (int(last[0].sum(dtype=torch.int64)) == int(last[3][0]) and
+              int((last[0] > 0).sum()) == G)
+    # a single synchronous call (copy-in, kernels, copy-out, wait): the latency of one batch
+    sync_ms = []
+    for i in range(5):
+        t1 = time.perf_counter()
+        _lib.check(L.othello_playout_host(ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), P(h_t0), ops.POLICY_RANDOM, 0, 0, 0, None,
+                                          -1, None, T_MAX, None, None, None, P(last[0]), P(last[1]), P(last[2])),
+                   "othello_playout_host")
+        sync_ms.append(1e3 * (time.perf_counter() - t1))
+        e2e_gid[0] += G
     L.othello_ctx_destroy(ctx)
     h2d = G * (8 + 8 + 1)
-    d2h = G * (4 + 8 + 8)
+    d2h = G * (4 + 8 + 8) + 32
+
+    # ---- the other two GPU workloads of BASELINE.json, each with its own figures ------------------
+    extra = {}
+    if not args.no_extra:
+        extra["config4"] = config4_extra(dev, rank, world)
+        extra["config5"] = config5_extra(dev, rank, world)
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     if world > 1:
@@ -390,9 +559,14 @@ def run_b200_arm(args):
                                  "algorithmic": "%d B written per position" % BYTES_PER_POSITION}},
             "e2e": {"value": e2e_positions / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "games_per_s": G * K * n_gpus / (e2e_ms * 1e-3),
-                    "api": "othello_playout_host (C ABI, pinned host buffers; trajectories stay in HBM)"},
+                    "ms_per_step": e2e_ms / K, "frac_of_value": (e2e_positions / e2e_ms) / (positions / total_ms),
+                    "sync_call_ms": min(sync_ms), "results_checked": bool(e2e_ok), "host_binding": binding,
+                    "api": "othello_playout_host_async + othello_ctx_wait (C ABI, pinned host buffers, two batches "
+                           "in flight; start positions uploaded and per-game results + totals downloaded every step; "
+                           "trajectories stay in HBM); sync_call_ms = one synchronous othello_playout_host call"},
             "gpu_launches": K,
             "step_kernel": step_info,
+            "extra": extra,
             "clocks": clocks,
         }
         if cb is not None:
@@ -415,6 +589,7 @@ def main():
                     help="seconds of host-core time per CPU sample (default: 12 for the cpu_baseline leg, "
                          "90 / (steps + warmup) clamped to [2, 20] per step of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 4 / config 5 objects")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                      # timing rule: at least 3 warm-up steps

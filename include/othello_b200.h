@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OTHELLO_ABI_VERSION 2
+#define OTHELLO_ABI_VERSION 3
 
 #define OTHELLO_EMPTY 0
 #define OTHELLO_BLACK 1
@@ -132,6 +132,11 @@ typedef struct {
     int32_t  policy_white;        /* White's engine, or -1 = the same as `policy` (which is then both players') */
     int32_t  reserved;
     const float *weights_white;   /* DEVICE float[4][10] for White's greedy engine, or NULL = `weights` */
+    /* what GameRunner.play_a_game reports at the end of a game (game_runner.py:194-199) and
+     * store_batch_stats sums over a batch (learn_base.py:70-88), accumulated (+=) over the games of
+     * this launch: [0] plies played, [1] sum of (n_black - n_white) as two's complement, [2] games Black
+     * won, [3] games White won.  DEVICE uint64[4] or NULL; the caller zeroes it. */
+    unsigned long long *totals;
 } othello_playout_args;
 
 int othello_playout(const othello_playout_args *args, void *stream);
@@ -150,12 +155,23 @@ int othello_perft(uint64_t black, uint64_t white, int turn, int depth, void *wor
 
 /* For every recorded position t of every game and both sides ('O' = Black then 'X' = White,
  * progress_position_moves_learn.py:44-47): x = (mobility, a..h, 1), y = (own - opp final discs) *
- * decay[nplies - t] (:55, decay[k] = 0.9 ** k computed by the host in fp64), accumulated per phase
- * shard into stats[4][112] (+=): XtX[10][10], Xty[10], n, sum y^2.  stats: DEVICE double, caller zeroes. */
+ * decay[nplies - t] (:55, decay[k] = 0.9 ** k computed by the host in fp64), accumulated (+=) per phase
+ * shard into EXACT integer accumulators acc[4][OTHELLO_ACC] (DEVICE int64, caller zeroes):
+ *   [0..54]  upper triangle of XtX[10][10], row-major (the sample count n is its last entry, 1 x 1);
+ *   [56+2k], [57+2k]  high / low word of the 2^-40 fixed-point sum k: Xty[0..8] for k = 0..8, sum y^2 for k = 9
+ *            (every game contributes its fp64 partial sums, formed in ply order, rounded once to 2^-40).
+ * Integer sums do not depend on the order of additions: the accumulators -- and therefore the learnt
+ * parameters -- are bit-identical however games are split over launches, ranks or GPUs, and the ranks'
+ * exchange is an all-reduce(SUM) of these 320 int64.  Games with nplies > t_max are skipped. */
+#define OTHELLO_ACC 80
 int othello_learn_accumulate(const uint64_t *traj_black, const uint64_t *traj_white, const int32_t *nplies,
                              const uint64_t *final_black, const uint64_t *final_white,
                              int64_t n_games, int64_t stride, int32_t t_max, const double *decay /* [t_max+1] */,
-                             double *stats, void *stream);
+                             int64_t *acc, void *stream);
+
+/* acc[4][OTHELLO_ACC] -> stats[4][OTHELLO_STATS] doubles (=): XtX[10][10], Xty[10], n, sum y^2; every
+ * value is the correctly rounded image of its exact integer sum.  DEVICE pointers. */
+int othello_learn_stats(const int64_t *acc, double *stats, void *stream);
 
 /* fit_parameter for the four shards ON the device (progress_position_moves_learn.py:160-184, minus
  * its sampling): OLS with intercept from stats[4][112] (minimum-norm when a shard is rank deficient),
@@ -211,9 +227,14 @@ int othello_legal_host(othello_ctx *ctx, const uint64_t *own, const uint64_t *op
 int othello_step_host(othello_ctx *ctx, uint64_t *black, uint64_t *white, uint8_t *turn, int32_t *nturn,
                       const uint8_t *move, uint64_t *flips_out, int32_t *ret, uint8_t *flags, int64_t n);
 
+/* tuning knobs of a context */
+#define OTHELLO_OPT_MAX_CHUNKS 1   /* playout batches are pipelined in at most this many chunks (default 8) */
+int othello_ctx_set_option(othello_ctx *ctx, int32_t option, int64_t value);
+
 /* play_a_game for n games from host-resident start positions (NULL = standard opening); the
  * trajectory stays in device memory owned by the context (othello_ctx_trajectory) unless host
- * trajectory pointers are given.  Per-game results come back to the host arrays. */
+ * trajectory pointers are given.  Per-game results come back to the host arrays.  Synchronous:
+ * othello_playout_host_async + othello_ctx_wait. */
 int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t n_games,
                          const uint64_t *black0, const uint64_t *white0, const uint8_t *turn0,
                          int32_t policy, int32_t random_plies, int32_t n_rand_black, int32_t n_rand_white,
@@ -222,7 +243,26 @@ int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t
                          uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move /* host or NULL */,
                          int32_t *nplies, uint64_t *final_black, uint64_t *final_white);
 
-/* device pointers of the last othello_playout_host trajectory ([t_max+1][n], [t_max+1][n], [t_max][n]) */
+/* The same, asynchronous: enqueues copy-in, kernels and copy-out and returns at once with a ticket;
+ * the host output arrays (and `totals`: HOST int64[4], the sums of othello_playout_args.totals for
+ * this batch, or NULL) are valid after othello_ctx_wait(ctx, ticket).  nplies / final_* may be NULL
+ * when the caller only wants `totals` or the device trajectory.  A context keeps two batches in
+ * flight: issue batch i+1, then wait for batch i, and the PCIe copies of one batch run under the
+ * kernels of the other.  Input arrays must stay untouched until the ticket has been waited for (use
+ * pinned memory -- pageable buffers make the copies synchronous).  Issuing a third batch reuses the
+ * device buffers of the first (stream-ordered; the caller need not have waited for it). */
+int othello_playout_host_async(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t n_games,
+                               const uint64_t *black0, const uint64_t *white0, const uint8_t *turn0,
+                               int32_t policy, int32_t random_plies, int32_t n_rand_black, int32_t n_rand_white,
+                               const float *weights, int32_t policy_white, const float *weights_white, int32_t t_max,
+                               uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move,
+                               int32_t *nplies, uint64_t *final_black, uint64_t *final_white,
+                               int64_t *totals, int64_t *ticket);
+int othello_ctx_wait(othello_ctx *ctx, int64_t ticket);
+
+/* device pointers of the most recently ISSUED playout's trajectory ([t_max+1][n], [t_max+1][n],
+ * [t_max][n]); valid once its ticket has been waited for and until two more playouts have been
+ * issued on the context (or a *_legal_host / *_step_host call reuses the workspace) */
 int othello_ctx_trajectory(othello_ctx *ctx, uint64_t **traj_black, uint64_t **traj_white, uint8_t **traj_move,
                            int64_t *stride, int32_t *t_max);
 

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libothello_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -31,7 +31,7 @@ class PlayoutArgs(ctypes.Structure):
         ("weights", vp), ("t_max", i32), ("stride", i64),
         ("traj_black", vp), ("traj_white", vp), ("traj_move", vp),
         ("nplies", vp), ("final_black", vp), ("final_white", vp),
-        ("policy_white", i32), ("reserved", i32), ("weights_white", vp),
+        ("policy_white", i32), ("reserved", i32), ("weights_white", vp), ("totals", vp),
     ]
 
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "othello_perft": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, i64,
                                      u64p, vp]),
     "othello_learn_accumulate": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp]),
+    "othello_learn_stats": (ctypes.c_int, [vp, vp, vp]),
     "othello_learn_solve": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "othello_value_records": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
     "othello_value_smooth": (ctypes.c_int, [vp, vp, vp, ctypes.c_double, vp, i64, vp]),
@@ -65,6 +66,11 @@ SIGNATURES = {
     "othello_step_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
     "othello_playout_host": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32, i32,
                                             vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "othello_playout_host_async": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32,
+                                                  i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp,
+                                                  ctypes.POINTER(i64)]),
+    "othello_ctx_wait": (ctypes.c_int, [vp, i64]),
+    "othello_ctx_set_option": (ctypes.c_int, [vp, i32, i64]),
     "othello_ctx_trajectory": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                               ctypes.POINTER(i64), ctypes.POINTER(i32)]),
 }

@@ -144,6 +144,28 @@ OBF_HD u64 legal_moves(u64 own, u64 opp)
     const Inter down = moves_up(rev_inter(o), rev_inter(p), rev_inter(m));   // the rotated board
     return from_inter(ior(up, rev_inter(down))) & ~(own | opp);
 }
+// n_puttable_for() of BOTH colours of one position (the mobility feature of counts(),
+// parameter_progress_position_moves_learn.py:8): the layout conversions and rotations of the two
+// boards are shared, and a popcount does not care about the layout, so nothing is converted back.
+OBF_HD void mobility_both(u64 black, u64 white, int &mob_black, int &mob_white)
+{
+    const Inter b = to_inter(black), w = to_inter(white);
+    const Inter mb = Inter{b.a & kInner32, b.b & kInner32}, mw = Inter{w.a & kInner32, w.b & kInner32};
+    const Inter br = rev_inter(b), wr = rev_inter(w);
+    // kInner32 is a palindrome, so the rotated inner mask is the same constant
+    const Inter mbr = Inter{br.a & kInner32, br.b & kInner32}, mwr = Inter{wr.a & kInner32, wr.b & kInner32};
+    const Inter empty = Inter{~(b.a | w.a), ~(b.b | w.b)};
+    const Inter lb = iand(ior(moves_up(b, w, mw), rev_inter(moves_up(br, wr, mwr))), empty);
+    const Inter lw = iand(ior(moves_up(w, b, mb), rev_inter(moves_up(wr, br, mbr))), empty);
+#if defined(__CUDA_ARCH__)
+    mob_black = __popc(lb.a) + __popc(lb.b);
+    mob_white = __popc(lw.a) + __popc(lw.b);
+#else
+    mob_black = __builtin_popcount(lb.a) + __builtin_popcount(lb.b);
+    mob_white = __builtin_popcount(lw.a) + __builtin_popcount(lw.b);
+#endif
+}
+
 // (own_r / opp_r = rev64(own / opp) are what flips_for needs; move generation rotates in its own layout)
 OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp); }
 

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     const int64_t stride = a.stride;
 
     int t = 0;
+    const bool live = !done;
+    int plies = 0, n_black = 0, n_white = 0;               // the game's result, for the launch totals
     while (__any_sync(kFull, !done)) {
         u64 legal = 0, own_r = 0, opp_r = 0;
         if (!done) {
@@ -89,9 +91,11 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
             legal = obf::legal_moves(own, opp, own_r, opp_r);
             if (legal == 0 && obf::legal_moves(opp, own, opp_r, own_r) == 0) {     // is_game_over (board.py:57-58)
                 done = true;
+                const u64 fb = black_moves ? own : opp, fw = black_moves ? opp : own;
                 a.nplies[g] = t;
-                a.final_black[g] = black_moves ? own : opp;
-                a.final_white[g] = black_moves ? opp : own;
+                a.final_black[g] = fb;
+                a.final_white[g] = fw;
+                plies = t; n_black = __popcll(fb); n_white = __popcll(fw);
             }
         }
         const bool moving = !done && legal != 0;              // otherwise: finished, or this ply is a pass
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
         }
         __syncwarp();
     }
+    add_totals(a.totals, live, plies, n_black, n_white);
 }
 
 }  // namespace

@@ -1,5 +1,5 @@
 // learn.cu -- sufficient statistics of the per-phase linear regression, straight from the
-// trajectories the playout kernel left in HBM.
+// trajectories the game kernels left in HBM.
 //
 // Replaces, on the data-parallel learning path, the reference's per-position Redis round trips
 // (__update_state_for_a_book / __update_state_map, progress_position_moves_learn.py:37-62) and
@@ -7,11 +7,22 @@
 // recorded position contributes, for both sides ('O' = Black, 'X' = White, :44-47), the sample
 //     x = (mobility, a..h, 1)            counts() features 1..9 (+ intercept column)
 //     y = (own - opp final discs) * 0.9 ** (last_turn - turn)               (:40-42,55)
-// to the normal equations of its disc-count shard (:112-113).  The 4 x 112 doubles are the only
-// thing ranks exchange (one NCCL all-reduce); the 10x10 solves are done by the host.
+// to the normal equations of its disc-count shard (:112-113).
 //
-// Reads 16 B per position (coalesced rows of the SoA trajectory); XtX is accumulated in integers
-// (exact), Xty / sum y^2 in fp64.
+// The statistics are accumulated as INTEGERS, so that they are identical -- bit for bit -- however
+// the games are split over launches, CTAs, ranks or GPUs, and the ranks' all-reduce is an exact
+// integer sum:
+//   * X^T X (and the sample count, its intercept x intercept entry) is a Gram matrix of small
+//     integers: a genuine dense contraction, so it runs on the tensor cores -- per warp and ply one
+//     16 x 16 x 64 int8 product (32 positions x 2 sides; mma.sync m16n8k32 s8, int32 accumulators);
+//   * X^T y and sum y^2 are fp64.  One lane owns one game and sums its positions in ply order, per
+//     shard and per block of plies -- a fixed order, whatever the launch geometry -- and hands every
+//     such partial sum over as a 2^-40 fixed-point integer (two int64 words).
+// othello_learn_stats turns the integers into the [4][112] doubles the solver reads.
+//
+// Work split: one CTA = 32 games, warp w of 8 = plies [w * chunk, (w + 1) * chunk): a warp reads
+// coalesced 256-byte rows of the SoA trajectory (16 B per position), and 2^16 games already give
+// every SM ~60 resident warps.
 #include "common.cuh"
 #include "fastboard.cuh"
 
@@ -19,50 +30,61 @@ using namespace ob;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kThreads = 32 * kWarps;
+constexpr int kGames = 32;                   // games per CTA (one per lane)
 constexpr int kX = 10;                       // regressors incl. intercept
-constexpr int kPairs = kX * (kX + 1) / 2;    // upper triangle of XtX
-constexpr int kF = kX + 2;                   // Xty[10], n, sum y^2
+constexpr int kFp = 10;                      // fp64 sums per shard: Xty[0..8] (Xty[9] is identically 0), sum y^2
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPairs = kX * (kX + 1) / 2;    // upper triangle of XtX
+constexpr int kFpBase = 56;                  // acc[shard][kFpBase + 2 k], [.. + 1] = high, low word of fp sum k
+constexpr double kFixScale = 1099511627776.0;            // 2^40
+static_assert(kFpBase >= kPairs && kFpBase + 2 * kFp <= OTHELLO_ACC, "accumulator layout");
 
 __host__ __device__ constexpr int pair_index(int i, int j) { return i * kX - i * (i - 1) / 2 + (j - i); }
 
-__device__ __forceinline__ double warp_sum_f64(double v)
+// D[16x8] += A[16x32] * B[32x8], signed 8-bit operands, 32-bit accumulators (tensor cores)
+__device__ __forceinline__ void mma_s8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
 {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Every lane keeps the statistics of the shard it is currently seeing in REGISTERS (55 integer
-// products on the FMA pipe + 12 fp64 sums per position) and spills them to the CTA's shared-memory
-// totals only when its shard changes -- tiles are walked in ply order, so that is ~4 times per lane --
-// and once at the end through warp reductions.
-struct LaneAcc {
-    unsigned xtx[kPairs];
-    double f[kF];
-    int shard;
+struct Gram {                                // the warp's 16 x 16 accumulator: columns 0..7 and 8..15
+    int lo[4], hi[4];
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++) lo[i] = hi[i] = 0;
+    }
 };
 
-__device__ __forceinline__ void lane_clear(LaneAcc &a, int shard)
+// hand the upper triangle of the warp's accumulator to the CTA totals of `shard`; every needed entry
+// is held by exactly one lane (fragment layout of m16n8k32: c0/c1 = row lane/4, columns 2 * (lane % 4) + {0, 1};
+// c2/c3 = row lane/4 + 8)
+__device__ __forceinline__ void gram_flush(const Gram &g, unsigned (*s_xtx)[kPairs], int shard, int lane)
 {
-#pragma unroll
-    for (int p = 0; p < kPairs; p++) a.xtx[p] = 0u;
-#pragma unroll
-    for (int k = 0; k < kF; k++) a.f[k] = 0.0;
-    a.shard = shard;
+    const int r = lane >> 2, c = 2 * (lane & 3);
+    if (r <= c && g.lo[0]) atomicAdd(&s_xtx[shard][pair_index(r, c)], (unsigned)g.lo[0]);
+    if (r <= c + 1 && g.lo[1]) atomicAdd(&s_xtx[shard][pair_index(r, c + 1)], (unsigned)g.lo[1]);
+    if ((lane & 3) == 0) {                   // columns 8 and 9
+        if (g.hi[0]) atomicAdd(&s_xtx[shard][pair_index(r, 8)], (unsigned)g.hi[0]);
+        if (g.hi[1]) atomicAdd(&s_xtx[shard][pair_index(r, 9)], (unsigned)g.hi[1]);
+        if (r == 0 && g.hi[2]) atomicAdd(&s_xtx[shard][pair_index(8, 8)], (unsigned)g.hi[2]);
+        if (r <= 1 && g.hi[3]) atomicAdd(&s_xtx[shard][pair_index(8 + r, 9)], (unsigned)g.hi[3]);
+    }
 }
 
-// a single lane hands its partial sums to the CTA totals (rare: shard change inside a lane)
-__device__ __forceinline__ void lane_spill(LaneAcc &a, unsigned long long (*s_xtx)[kPairs], double (*s_f)[kF])
+// a lane's fp64 partial sums of one (game, ply block, shard) -> 2^-40 fixed point, exact integer adds from here on
+__device__ __forceinline__ void fp_flush(const double (&f)[kFp], unsigned long long (*s_fp)[2 * kFp], int shard)
 {
-    if (a.shard >= 0) {
 #pragma unroll
-        for (int p = 0; p < kPairs; p++)
-            if (a.xtx[p]) atomicAdd(&s_xtx[a.shard][p], (unsigned long long)a.xtx[p]);
-#pragma unroll
-        for (int k = 0; k < kF; k++)
-            if (a.f[k] != 0.0) atomicAdd(&s_f[a.shard][k], a.f[k]);
+    for (int k = 0; k < kFp; k++) {
+        if (f[k] == 0.0) continue;
+        const long long q = __double2ll_rn(f[k] * kFixScale);
+        atomicAdd(&s_fp[shard][2 * k], (unsigned long long)(q >> 32));               // signed high part
+        atomicAdd(&s_fp[shard][2 * k + 1], (unsigned long long)(q & 0xffffffffll));  // unsigned low 32 bits
     }
 }
 
@@ -72,82 +94,130 @@ __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__
                                                          const u64 *__restrict__ final_black,
                                                          const u64 *__restrict__ final_white, int64_t n_games,
                                                          int64_t stride, int t_max, const double *__restrict__ decay,
-                                                         double *__restrict__ stats)
+                                                         unsigned long long *__restrict__ acc)
 {
-    __shared__ unsigned long long s_xtx[OTHELLO_PHASES][kPairs];
-    __shared__ double s_f[OTHELLO_PHASES][kF];
-    for (int i = threadIdx.x; i < OTHELLO_PHASES * kPairs; i += kThreads) (&s_xtx[0][0])[i] = 0ull;
-    for (int i = threadIdx.x; i < OTHELLO_PHASES * kF; i += kThreads) (&s_f[0][0])[i] = 0.0;
+    __shared__ unsigned s_xtx[OTHELLO_PHASES][kPairs];
+    __shared__ unsigned long long s_fp[OTHELLO_PHASES][2 * kFp];
+    // feature bytes of the warp's 32 positions, [side][feature][position]: the K-major operand of the Gram product
+    __shared__ unsigned stage[kWarps][2][kX][8];
+    for (int i = threadIdx.x; i < OTHELLO_PHASES * kPairs; i += kThreads) (&s_xtx[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < OTHELLO_PHASES * 2 * kFp; i += kThreads) (&s_fp[0][0])[i] = 0ull;
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int64_t tiles_per_row = (n_games + kThreads - 1) / kThreads;
-    const int64_t tiles = tiles_per_row * (int64_t)(t_max + 1);
-    // contiguous, ply-major ranges of tiles per CTA: the shard changes a handful of times per lane
-    const int64_t first = tiles * blockIdx.x / gridDim.x, last = tiles * (blockIdx.x + 1) / gridDim.x;
-    LaneAcc acc;
-    lane_clear(acc, -1);
-    for (int64_t tile = first; tile < last; tile++) {
-        const int t = (int)(tile / tiles_per_row);
-        const int64_t g = (tile % tiles_per_row) * kThreads + threadIdx.x;
-        int len = -1;
-        if (g < n_games) len = nplies[g];
-        if (t > len || len > t_max) continue;                 // positions 0..nplies are recorded; truncated games are skipped
-        const u64 b = traj_black[(int64_t)t * stride + g], w = traj_white[(int64_t)t * stride + g];
-        const int shard = phase_row(__popcll(b | w));
-        if (shard != acc.shard) { lane_spill(acc, s_xtx, s_f); lane_clear(acc, shard); }
-        int xb[kX], xw[kX];
-        const u64 br = obf::rev64(b), wr = obf::rev64(w);
-        xb[0] = __popcll(obf::legal_moves(b, w, br, wr));
-        xw[0] = __popcll(obf::legal_moves(w, b, wr, br));
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            xb[1 + k] = __popcll(b & kClassMask[k]);
-            xw[1 + k] = __popcll(w & kClassMask[k]);
-        }
-        xb[9] = xw[9] = 1;
-        const int value = __popcll(final_black[g]) - __popcll(final_white[g]);       // value_for_black (:40-42)
-        const double y = (double)value * decay[len - t];                             // * l ** turn_left (:55)
-        // XtX: both sides at once, exact integer sums
-#pragma unroll
-        for (int i = 0; i < kX; i++) {
-#pragma unroll
-            for (int j = i; j < kX; j++) acc.xtx[pair_index(i, j)] += (unsigned)(xb[i] * xb[j] + xw[i] * xw[j]);
-        }
-        // Xty: White's target is the negative of Black's (value_for_white, :42)
-#pragma unroll
-        for (int i = 0; i < kX; i++) acc.f[i] += (double)(xb[i] - xw[i]) * y;
-        acc.f[kX] += 2.0;
-        acc.f[kX + 1] += 2.0 * y * y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * kGames + lane;
+    int len = -1;
+    if (g < n_games) {
+        len = nplies[g];
+        if (len > t_max) len = -1;                            // truncated games are skipped
     }
-    // end of the CTA's range: reduce over the warp per shard, one atomic per value per warp
-#pragma unroll 1
-    for (int s = 0; s < OTHELLO_PHASES; s++) {
-        const bool in = acc.shard == s;
-        if (!__any_sync(kFull, in)) continue;
+    double value = 0.0;
+    if (len >= 0) value = (double)(__popcll(final_black[g]) - __popcll(final_white[g]));   // value_for_black (:40-42)
+    const int chunk = (t_max + 1 + kWarps - 1) / kWarps;
+    const int t0 = warp * chunk;
+    int t1 = min(t0 + chunk, t_max + 1);
+    t1 = min(t1, __reduce_max_sync(kFull, len) + 1);          // positions 0..nplies are recorded
+
+    Gram gram;
+    gram.clear();
+    int cur = -1;                                             // shard of the warp's Gram accumulator
+    double f[kFp];
 #pragma unroll
-        for (int p = 0; p < kPairs; p++) {
-            // 32 lanes x (tiles per CTA) x 2 * 64 * 64 stays far below 2^32
-            const unsigned r = __reduce_add_sync(kFull, in ? acc.xtx[p] : 0u);
-            if (lane == (p & 31) && r) atomicAdd(&s_xtx[s][p], (unsigned long long)r);
+    for (int k = 0; k < kFp; k++) f[k] = 0.0;
+    int mine = -1;                                            // shard of the lane's fp64 partial sums
+    unsigned char *stage_b = (unsigned char *)&stage[warp][0][0][0];
+    const int fr = lane >> 2, fc = lane & 3;                  // fragment row / column group of this lane
+
+    for (int t = t0; t < t1; t++) {
+        const bool live = t <= len;
+        int x[2][kX - 1];
+        int shard = -1;
+        if (live) {
+            const u64 b = traj_black[(int64_t)t * stride + g], w = traj_white[(int64_t)t * stride + g];
+            shard = phase_row(__popcll(b | w));
+            obf::mobility_both(b, w, x[0][0], x[1][0]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                x[0][1 + k] = __popcll(b & kClassMask[k]);
+                x[1][1 + k] = __popcll(w & kClassMask[k]);
+            }
+            if (shard != mine) {
+                if (mine >= 0) fp_flush(f, s_fp, mine);
+#pragma unroll
+                for (int k = 0; k < kFp; k++) f[k] = 0.0;
+                mine = shard;
+            }
+            const double y = value * __ldg(decay + (len - t));                        // * l ** turn_left (:55)
+            // White's target is the negative of Black's (value_for_white, :42); the intercept terms cancel
+#pragma unroll
+            for (int k = 0; k < kX - 1; k++) f[k] += (double)(x[0][k] - x[1][k]) * y;
+            f[kFp - 1] += 2.0 * (y * y);
         }
+        // X^T X of the warp's positions, shard by shard (one shard unless games with passes straddle a boundary)
+        unsigned todo = __ballot_sync(kFull, live);
+        while (todo) {
+            const int s = __shfl_sync(kFull, shard, __ffs(todo) - 1);
+            const unsigned grp = __ballot_sync(kFull, live && shard == s);
+            todo &= ~grp;
+            if (s != cur) {
+                if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
+                gram.clear();
+                cur = s;
+            }
+            const bool in = (grp >> lane) & 1u;
 #pragma unroll
-        for (int k = 0; k < kF; k++) {
-            const double r = warp_sum_f64(in ? acc.f[k] : 0.0);
-            if (lane == k && r != 0.0) atomicAdd(&s_f[s][k], r);
+            for (int side = 0; side < 2; side++) {
+#pragma unroll
+                for (int k = 0; k < kX - 1; k++) stage_b[(side * kX + k) * 32 + lane] = (unsigned char)(in ? x[side][k] : 0);
+                stage_b[(side * kX + kX - 1) * 32 + lane] = in ? 1 : 0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const unsigned a0 = stage[warp][side][fr][fc], a2 = stage[warp][side][fr][4 + fc];
+                const unsigned a1 = fr < 2 ? stage[warp][side][8 + fr][fc] : 0u;
+                const unsigned a3 = fr < 2 ? stage[warp][side][8 + fr][4 + fc] : 0u;
+                mma_s8(gram.lo, a0, a1, a2, a3, a0, a2);       // columns = features 0..7
+                mma_s8(gram.hi, a0, a1, a2, a3, a1, a3);       // columns = features 8, 9
+            }
+            __syncwarp();
         }
     }
+    if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
+    if (mine >= 0) fp_flush(f, s_fp, mine);
     __syncthreads();
-    for (int i = threadIdx.x; i < OTHELLO_PHASES * OTHELLO_STATS; i += kThreads) {
-        const int s = i / OTHELLO_STATS, k = i % OTHELLO_STATS;
+    for (int i = threadIdx.x; i < OTHELLO_PHASES * OTHELLO_ACC; i += kThreads) {
+        const int s = i / OTHELLO_ACC, k = i % OTHELLO_ACC;
+        unsigned long long v = 0ull;
+        if (k < kPairs) v = s_xtx[s][k];
+        else if (k >= kFpBase && k < kFpBase + 2 * kFp) v = s_fp[s][k - kFpBase];
+        if (v) atomicAdd(&acc[i], v);
+    }
+}
+
+// integers -> the doubles the solver reads: stats[s] = XtX[10][10], Xty[10], n, sum y^2
+__global__ void __launch_bounds__(128) stats_kernel(const long long *__restrict__ acc, double *__restrict__ stats)
+{
+    const int s = blockIdx.x;
+    const long long *a = acc + s * OTHELLO_ACC;
+    double *out = stats + s * OTHELLO_STATS;
+    for (int k = threadIdx.x; k < OTHELLO_STATS; k += blockDim.x) {
         double v;
         if (k < kX * kX) {
-            const int a = k / kX, b = k % kX;
-            v = (double)s_xtx[s][a <= b ? pair_index(a, b) : pair_index(b, a)];
+            const int i = k / kX, j = k % kX;
+            v = (double)a[i <= j ? pair_index(i, j) : pair_index(j, i)];
+        } else if (k == 110) {
+            v = (double)a[pair_index(kX - 1, kX - 1)];        // n = sum of intercept * intercept
         } else {
-            v = s_f[s][k - kX * kX];
+            const int q = k == 111 ? kFp - 1 : k - kX * kX;    // sum y^2 | Xty[q]
+            if (q == kX - 1 && k != 111) { out[k] = 0.0; continue; }                 // Xty[intercept] cancels exactly
+            long long hi = a[kFpBase + 2 * q];
+            unsigned long long lo = (unsigned long long)a[kFpBase + 2 * q + 1];
+            hi += (long long)(lo >> 32);                       // normalise: exact integer arithmetic
+            lo &= 0xffffffffull;
+            v = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / kFixScale);        // one rounding
         }
-        if (v != 0.0) atomicAdd(&stats[i], v);
+        out[k] = v;
     }
 }
 
@@ -155,19 +225,24 @@ __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__
 
 extern "C" int othello_learn_accumulate(const uint64_t *traj_black, const uint64_t *traj_white, const int32_t *nplies,
                                         const uint64_t *final_black, const uint64_t *final_white, int64_t n_games,
-                                        int64_t stride, int32_t t_max, const double *decay, double *stats, void *stream)
+                                        int64_t stride, int32_t t_max, const double *decay, int64_t *acc, void *stream)
 {
-    OB_CHECK_ARGS(n_games >= 0 && t_max >= 0 && stats && decay);
+    OB_CHECK_ARGS(n_games >= 0 && t_max >= 0 && acc && decay);
     if (n_games == 0) return 0;
     OB_CHECK_ARGS(traj_black && traj_white && nplies && final_black && final_white && stride >= n_games);
-    const int64_t tiles = ((n_games + kThreads - 1) / kThreads) * (int64_t)(t_max + 1);
-    int dev = 0, sms = 148;
-    OB_CUDA(cudaGetDevice(&dev));
-    OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t want = (int64_t)sms * 4;
-    const unsigned blocks = (unsigned)(tiles < want ? tiles : want);
-    learn_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>((const u64 *)traj_black, (const u64 *)traj_white, nplies,
-                                                               (const u64 *)final_black, (const u64 *)final_white,
-                                                               n_games, stride, t_max, decay, stats);
+    // a warp's int32 Gram accumulators hold at most chunk * 32 positions * 2 sides * 64^2 < 2^31
+    OB_CHECK_ARGS(t_max < 8 * kWarps * 128);
+    const int64_t blocks = (n_games + kGames - 1) / kGames;
+    OB_CHECK_ARGS(blocks <= 0x7fffffff);
+    learn_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        (const u64 *)traj_black, (const u64 *)traj_white, nplies, (const u64 *)final_black, (const u64 *)final_white,
+        n_games, stride, t_max, decay, (unsigned long long *)acc);
+    return ob_launch_status();
+}
+
+extern "C" int othello_learn_stats(const int64_t *acc, double *stats, void *stream)
+{
+    OB_CHECK_ARGS(acc && stats);
+    stats_kernel<<<OTHELLO_PHASES, 128, 0, (cudaStream_t)stream>>>((const long long *)acc, stats);
     return ob_launch_status();
 }

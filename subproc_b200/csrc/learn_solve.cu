@@ -15,8 +15,10 @@ namespace {
 constexpr int kN = 9;                       // regressors without the intercept
 constexpr int kSweeps = 16;
 
-__global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ stats, const float *__restrict__ prev_weights,
-                                                   float *__restrict__ weights, int32_t *__restrict__ params,
+// (prev_weights and weights may be the same table -- a shard without samples copies its own row -- so
+// neither carries __restrict__)
+__global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ stats, const float *prev_weights,
+                                                   float *weights, int32_t *__restrict__ params,
                                                    double *__restrict__ fits, double rcond)
 {
     __shared__ double A[kN][kN], V[kN][kN], sxy[kN], coef[kN], xbar[kN], lam_inv[kN];

@@ -74,32 +74,38 @@ __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_pla
     __syncthreads();
     const Rays rays = {ray_s};
     const int64_t gi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (gi >= a.n_games) return;
+    const bool live = gi < a.n_games;                  // lanes past the batch only take part in the totals
+    int plies = 0, n_black = 0, n_white = 0;
+    if (live) {
+        const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
+        const u64 w0 = a.white0 ? a.white0[gi] : OTHELLO_START_WHITE;
+        bool black_moves = UNIFORM ? true : (a.turn0[gi] == OTHELLO_BLACK);
+        Game g;
+        g.own = black_moves ? b0 : w0; g.opp = black_moves ? w0 : b0;
+        g.tb = TRAJ ? (u64 *)a.traj_black + gi : nullptr;
+        g.tw = TRAJ ? (u64 *)a.traj_white + gi : nullptr;
+        g.tm = TRAJ ? a.traj_move + gi : nullptr;
+        g.t = 0;
+        const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
+        const int t_max = a.t_max;
+        const int64_t stride = a.stride;
 
-    const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
-    const u64 w0 = a.white0 ? a.white0[gi] : OTHELLO_START_WHITE;
-    bool black_moves = UNIFORM ? true : (a.turn0[gi] == OTHELLO_BLACK);
-    Game g;
-    g.own = black_moves ? b0 : w0; g.opp = black_moves ? w0 : b0;
-    g.tb = TRAJ ? (u64 *)a.traj_black + gi : nullptr;
-    g.tw = TRAJ ? (u64 *)a.traj_white + gi : nullptr;
-    g.tm = TRAJ ? a.traj_move + gi : nullptr;
-    g.t = 0;
-    const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
-    const int t_max = a.t_max;
-    const int64_t stride = a.stride;
-
-    if (UNIFORM) {
-        for (;;) {
-            if (!play_ply<TRAJ, 1>(g, true, key, t_max, stride, rays)) { black_moves = true; break; }
-            if (!play_ply<TRAJ, 0>(g, false, key, t_max, stride, rays)) { black_moves = false; break; }
+        if (UNIFORM) {
+            for (;;) {
+                if (!play_ply<TRAJ, 1>(g, true, key, t_max, stride, rays)) { black_moves = true; break; }
+                if (!play_ply<TRAJ, 0>(g, false, key, t_max, stride, rays)) { black_moves = false; break; }
+            }
+        } else {
+            while (play_ply<TRAJ, -1>(g, black_moves, key, t_max, stride, rays)) black_moves = !black_moves;
         }
-    } else {
-        while (play_ply<TRAJ, -1>(g, black_moves, key, t_max, stride, rays)) black_moves = !black_moves;
+        const u64 fb = black_moves ? g.own : g.opp, fw = black_moves ? g.opp : g.own;
+        a.nplies[gi] = g.t;
+        a.final_black[gi] = fb;
+        a.final_white[gi] = fw;
+        plies = g.t; n_black = __popcll(fb); n_white = __popcll(fw);
     }
-    a.nplies[gi] = g.t;
-    a.final_black[gi] = black_moves ? g.own : g.opp;
-    a.final_white[gi] = black_moves ? g.opp : g.own;
+    __syncwarp();
+    add_totals(a.totals, live, plies, n_black, n_white);
 }
 
 int launch(const othello_playout_args &a, cudaStream_t s)

@@ -32,6 +32,25 @@ __device__ __forceinline__ bool substitute_now(u32 key, int t, int rest)
     return rest > 0 && ob::rng_below(ob::rng_draw(key, (u32)t, 0u), (u32)rest) == 0;
 }
 
+// End of a game kernel: what play_a_game reports per game (game_runner.py:194-199), summed over the
+// launch (othello_playout_args.totals).  Every lane of the warp must arrive (live = false for lanes
+// past the batch); one atomic per value per warp.
+__device__ __forceinline__ void add_totals(unsigned long long *totals, bool live, int plies, int n_black, int n_white)
+{
+    if (totals == nullptr) return;                     // uniform over the launch
+    constexpr unsigned kAll = 0xffffffffu;
+    const int p = __reduce_add_sync(kAll, live ? plies : 0);
+    const int d = __reduce_add_sync(kAll, live ? n_black - n_white : 0);
+    const int bw = __popc(__ballot_sync(kAll, live && n_black > n_white));
+    const int ww = __popc(__ballot_sync(kAll, live && n_white > n_black));
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(totals + 0, (unsigned long long)p);
+        atomicAdd(totals + 1, (unsigned long long)(long long)d);
+        atomicAdd(totals + 2, (unsigned long long)bw);
+        atomicAdd(totals + 3, (unsigned long long)ww);
+    }
+}
+
 }  // namespace obp
 
 // greedy.cu

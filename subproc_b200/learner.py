@@ -82,9 +82,39 @@ def stored_parameters(params_rows):
     return [int(x) for row in params_rows for x in row]
 
 
+N_ACC = 80                                                      # OTHELLO_ACC (include/othello_b200.h)
+_KX = 10
+_FP_BASE = 56
+
+
+def _pair(i, j):
+    return i * _KX - i * (i - 1) // 2 + (j - i)
+
+
+def stats_from_acc(acc):
+    """othello_learn_stats on the host: exact integer accumulators [4][80] (numpy / CPU tensor) -> the
+    [4][112] doubles (XtX[10][10], Xty[10], n, sum y^2), each the correctly rounded image of its integer
+    sum (Python integers: no intermediate rounding)."""
+    if hasattr(acc, "detach"):
+        acc = acc.detach().cpu().numpy()
+    acc = np.asarray(acc, dtype=np.int64).reshape(4, N_ACC)
+    out = np.zeros((4, N_STATS), dtype=np.float64)
+    for s in range(4):
+        a = [int(v) for v in acc[s]]
+        for i in range(_KX):
+            for j in range(_KX):
+                out[s, i * _KX + j] = float(a[_pair(min(i, j), max(i, j))])
+        out[s, 110] = float(a[_pair(9, 9)])
+        for k in range(10):                                     # Xty[0..8], then sum y^2
+            total = (a[_FP_BASE + 2 * k] << 32) + a[_FP_BASE + 2 * k + 1]
+            out[s, 111 if k == 9 else 100 + k] = total / float(1 << 40)      # int / float: one rounding
+    return out
+
+
 def allreduce_stats(stats):
-    """sum the per-rank statistics over all ranks (NCCL for CUDA tensors, gloo for CPU tensors).
-    A no-op in a single process."""
+    """sum the per-rank statistics / accumulators over all ranks (NCCL for CUDA tensors, gloo for CPU
+    tensors).  A no-op in a single process.  On the int64 accumulators the sum is exact, so every rank
+    count gives the same bits; on doubles it is the usual tolerance-level reduction."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
@@ -163,9 +193,22 @@ class ProgressPositionMovesLearn(object):
         return self.last_batch_stats
 
     # ---- one learning iteration ------------------------------------------------------------
-    def accumulate(self, playout, stats=None):
+    def accumulate(self, playout, acc=None):
+        """exact integer accumulators int64 [4][80] of a playout's trajectories (+= into ``acc``)"""
         from . import ops
-        return ops.learn_accumulate(playout, stats=stats, lam=self.l)
+        return ops.learn_accumulate(playout, acc=acc, lam=self.l)
+
+    def learn_from_acc(self, acc, book_id=None):
+        """all-reduce of the exact accumulators (320 int64 -- the ranks' only exchange, replacing the Redis
+        `fitting:*` polling of progress_position_moves_learn.py:131-150) -> statistics -> refit.  Integer
+        sums: the learnt parameters are identical for every rank count."""
+        acc = allreduce_stats(acc)
+        if getattr(acc, "is_cuda", False):
+            from . import ops
+            stats = ops.learn_stats(acc)
+        else:
+            stats = stats_from_acc(acc)
+        return self._refit(stats, book_id)
 
     def fit_parameter(self, phase_from, phase_to):
         """(mse, score, param, nsample) of one shard, like the reference's worker job (:160-184),
@@ -175,8 +218,11 @@ class ProgressPositionMovesLearn(object):
         return fit['rmse'], fit['r2'], scale_param(fit['coef']), fit['n']
 
     def learn_from_stats(self, stats, book_id=None):
-        """all-reduce -> 4 solves -> scale to +-127 -> int() -> stored parameters"""
-        stats = allreduce_stats(stats)
+        """all-reduce of fp64 statistics [4][112] -> 4 solves -> scale to +-127 -> int() -> stored
+        parameters (for statistics that do not come from the accumulators, e.g. samples of the value table)"""
+        return self._refit(allreduce_stats(stats), book_id)
+
+    def _refit(self, stats, book_id=None):
         self.last_stats = stats
         self.last_fits = fit_from_stats(stats)
         rows = []
@@ -196,28 +242,31 @@ class ProgressPositionMovesLearn(object):
         """config 5 without host round trips: every iteration is playout -> statistics -> all-reduce ->
         othello_learn_solve -> the next playout reads the new table straight from device memory.  The
         host only enqueues; parameters are copied back once at the end.  Same arithmetic as
-        ``self_play_iteration`` (the integer parameters may differ by one where a scaled coefficient
-        sits on an integer boundary: two eigen-solvers, last-ulp differences)."""
+        ``self_play_iteration`` on identical statistics (the integer parameters may differ by one where a
+        scaled coefficient sits on an integer boundary: two eigen-solvers, last-ulp differences)."""
         import torch
         from . import ops
         dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         w = torch.from_numpy(self.weights_table()).to(dev)
-        stats = torch.zeros((4, 112), dtype=torch.float64, device=dev)
+        acc = torch.zeros((4, N_ACC), dtype=torch.int64, device=dev)
+        stats = torch.empty((4, 112), dtype=torch.float64, device=dev)
         po = params = fits = None
         for it in range(first_iteration, first_iteration + n_iterations):
             gid0 = (it * world + rank) * games_per_rank
             po = ops.playout(games_per_rank, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
                              random_plies=random_plies, weights=w, t_max=t_max, out=po)
-            stats.zero_()
-            ops.learn_accumulate(po, stats=stats, lam=self.l)
-            allreduce_stats(stats)
-            w, params, fits = ops.learn_solve(stats, w, weights_out=w)
+            acc.zero_()
+            ops.learn_accumulate(po, acc=acc, lam=self.l)
+            allreduce_stats(acc)
+            ops.learn_stats(acc, out=stats)
+            w, params, fits = ops.learn_solve(stats, w, weights_out=w)     # in place: the solver allows the alias
         self.params = [int(v) for v in params.cpu().tolist()]
         f = fits.cpu().numpy()
         self.last_fits = [dict(coef=f[s, :9].copy(), intercept=float(f[s, 9]), rmse=float(f[s, 10]), r2=float(f[s, 11]),
                                n=int(f[s, 12])) for s in range(4)]
         self.last_stats = stats
-        self.last_processed_id = ((first_iteration + n_iterations - 1) * world + rank + 1) * games_per_rank - 1
+        # the id of the last game of the last iteration over ALL ranks, so every rank's checkpoint agrees
+        self.last_processed_id = (first_iteration + n_iterations) * world * games_per_rank - 1
         return po
 
     # ---- checkpoint / resume ------------------------------------------------------------------
@@ -287,8 +336,11 @@ class ProgressPositionMovesLearn(object):
                 at += count
             self.table.update(torch.from_numpy(keys).to(dev), torch.from_numpy(vals).to(dev))
         mses, scores, params, nsamples = [], [], [], []
+        old = np.asarray(self.read_parameters()[1:], dtype=np.float64).reshape(4, 9)
         for s, (lo, hi) in enumerate(PHASE_SHARDS):
             mse, score, param, nsample = self.table.fit_parameter(lo, hi, num=sample, seed=seed + s)
+            if nsample == 0:                                   # nothing seen in this phase yet: keep the stored row
+                param = tuple(float(v) for v in old[s])
             mses.append(mse); scores.append(score); params.append(param); nsamples.append(nsample)
         self.params = stored_parameters(params)
         self.last_processed_id = last_book_id
@@ -305,6 +357,6 @@ class ProgressPositionMovesLearn(object):
         gid0 = (iteration * world + rank) * games_per_rank
         po = ops.playout(games_per_rank, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
                          random_plies=random_plies, weights=w, t_max=t_max)
-        stats = self.accumulate(po)
-        rows = self.learn_from_stats(stats, book_id=gid0 + games_per_rank - 1)
+        acc = self.accumulate(po)
+        rows = self.learn_from_acc(acc, book_id=(iteration + 1) * world * games_per_rank - 1)
         return po, rows

@@ -207,11 +207,14 @@ class Playout:
 
 def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn0=None, policy=POLICY_RANDOM,
             random_plies=0, n_rand_black=0, n_rand_white=0, weights=None, t_max=T_MAX_DEFAULT, trajectory=True,
-            out=None, policy_white=None, weights_white=None):
+            out=None, policy_white=None, weights_white=None, totals=None):
     """GameRunner.play_a_game (game_runner.py:165-201) for n_games games in ONE kernel launch.
 
     Game g draws from the counter-based stream (seed, gid0 + g): sharding games over launches or
     GPUs does not change any game.  ``out`` may be a previous Playout of the same shape to reuse.
+    ``totals``: optional int64 [4] device tensor, += (plies, sum of n_black - n_white, Black wins, White
+    wins) over the games of this launch -- what play_a_game / store_batch_stats report
+    (game_runner.py:194-199, learn_base.py:70-88).
     """
     if device is None:
         device = black0.device if black0 is not None else torch.device("cuda", torch.cuda.current_device())
@@ -239,6 +242,7 @@ def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn
     a.nplies = _req(out.nplies, torch.int32, n, "nplies")
     a.final_black = _req(out.final_black, torch.int64, n, "final_black")
     a.final_white = _req(out.final_white, torch.int64, n, "final_white")
+    a.totals = _opt(totals, torch.int64, 4, "totals")
     with torch.cuda.device(device):
         _lib.check(_lib.lib().othello_playout(ctypes.byref(a), _stream(out.nplies)), "othello_playout")
     return out
@@ -268,14 +272,29 @@ def decay_table(t_max, lam=0.90):
     return np.array([lam ** k for k in range(t_max + 1)], dtype=np.float64)
 
 
-def learn_accumulate(po, stats=None, lam=0.90):
-    """Per-shard normal-equation statistics [4][112] (float64) of a Playout's trajectories."""
+N_ACC = 80                                       # OTHELLO_ACC: exact integer accumulators per phase shard
+_decay_cache = {}
+
+
+def decay_tensor(t_max, lam, device):
+    """decay_table on the device, uploaded once per (t_max, lam, device)"""
+    key = (int(t_max), float(lam), str(device))
+    t = _decay_cache.get(key)
+    if t is None:
+        t = _decay_cache[key] = torch.from_numpy(decay_table(t_max, lam)).to(device)
+    return t
+
+
+def learn_accumulate(po, acc=None, lam=0.90):
+    """Exact per-shard normal-equation accumulators int64 [4][80] (+=) of a Playout's trajectories
+    (include/othello_b200.h: othello_learn_accumulate).  Integer sums: additive over any split of the
+    games, bit for bit; ``learn_stats`` turns them into the doubles the solvers read."""
     dev = po.nplies.device
     if po.black is None:
         raise ValueError("learn_accumulate needs a Playout with trajectories")
-    if stats is None:
-        stats = torch.zeros((4, 112), dtype=torch.float64, device=dev)
-    decay = torch.from_numpy(decay_table(po.t_max, lam)).to(dev)
+    if acc is None:
+        acc = torch.zeros((4, N_ACC), dtype=torch.int64, device=dev)
+    decay = decay_tensor(po.t_max, lam, dev)
     n = po.n_games
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().othello_learn_accumulate(
@@ -283,9 +302,19 @@ def learn_accumulate(po, stats=None, lam=0.90):
             _req(po.white, torch.int64, (po.t_max + 1) * n, "traj_white"),
             _req(po.nplies, torch.int32, n, "nplies"), _req(po.final_black, torch.int64, n, "final_black"),
             _req(po.final_white, torch.int64, n, "final_white"), n, n, po.t_max,
-            _req(decay, torch.float64, po.t_max + 1, "decay"), _req(stats, torch.float64, 448, "stats"),
-            _stream(stats)), "othello_learn_accumulate")
-    return stats
+            _req(decay, torch.float64, po.t_max + 1, "decay"), _req(acc, torch.int64, 4 * N_ACC, "acc"),
+            _stream(acc)), "othello_learn_accumulate")
+    return acc
+
+
+def learn_stats(acc, out=None):
+    """accumulators int64 [4][80] -> statistics float64 [4][112] (XtX[10][10], Xty[10], n, sum y^2)"""
+    out = torch.empty((4, 112), dtype=torch.float64, device=acc.device) if out is None else out
+    with torch.cuda.device(acc.device):
+        _lib.check(_lib.lib().othello_learn_stats(_req(acc, torch.int64, 4 * N_ACC, "acc"),
+                                                  _req(out, torch.float64, 448, "stats"), _stream(acc)),
+                   "othello_learn_stats")
+    return out
 
 
 def learn_solve(stats, prev_weights, weights_out=None):

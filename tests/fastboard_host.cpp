@@ -28,3 +28,8 @@ extern "C" void fb_flips(const unsigned long long *own, const unsigned long long
                  : obf::flips_for(sq[i], own[i], opp[i], obf::rev64(own[i]), obf::rev64(opp[i]), Rays());
     }
 }
+
+extern "C" void fb_mobility_both(const unsigned long long *black, const unsigned long long *white, int *mb, int *mw, long n)
+{
+    for (long i = 0; i < n; i++) obf::mobility_both(black[i], white[i], mb[i], mw[i]);
+}

@@ -42,7 +42,14 @@ def test_b200_arm_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"] < 1.2
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["hbm"]["peak"] > 1000
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 131072 * 17 and e["d2h_bytes_per_step"] == 131072 * 20
-    assert e["value"] <= d["value"] * 1.05
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 131072 * 17 and e["d2h_bytes_per_step"] == 131072 * 20 + 32
+    assert e["results_checked"] is True
+    # (chunked launches on rotating streams hide the tail of one launch behind the next: e2e may edge past `value`)
+    assert e["value"] <= d["value"] * 1.15
+    c4, c5 = d["extra"]["config4"], d["extra"]["config5"]
+    assert c4["positions_per_s"] > 0 and c4["children_per_s"] > c4["positions_per_s"]
+    assert c5["parity"] == {"allreduced_accumulators_equal_rank0_replay_of_all_game_ids": True,
+                            "parameters_identical_on_all_ranks": True}
+    assert c5["allreduce_bytes"] == 2560 and len(c5["parameters"]) == 36
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
     assert d["clocks"]["sm_mhz"] is None or d["clocks"]["sm_mhz"] > 500

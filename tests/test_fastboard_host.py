@@ -72,3 +72,18 @@ def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
     _, _, want, ret = oracle.put(own, opp, 1, sq)
     assert np.array_equal(out, want)
     assert (ret >= 6).sum() > 50 and (ret == 0).sum() > 1000          # six-disc runs and dead rays are both present
+
+
+def test_mobility_of_both_colours_in_one_pass(fb, oracle):
+    """obf::mobility_both (shared conversions, popcount in the interleaved layout) == popcount of puttables()"""
+    b, w = positions(oracle, 300, 52)
+    rng = np.random.RandomState(3)
+    occ = rng.randint(0, 2 ** 62, size=5000).astype(np.uint64) | (rng.randint(0, 4, size=5000).astype(np.uint64) << np.uint64(62))
+    col = rng.randint(0, 2 ** 62, size=5000).astype(np.uint64) | (rng.randint(0, 4, size=5000).astype(np.uint64) << np.uint64(62))
+    b = np.ascontiguousarray(np.concatenate([b, occ & col]))
+    w = np.ascontiguousarray(np.concatenate([w, occ & ~col]))
+    n = b.size
+    mb, mw = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    fb.fb_mobility_both(P(b), P(w), P(mb), P(mw), ctypes.c_long(n))
+    pop = lambda a: np.array([bin(int(v)).count("1") for v in a], dtype=np.int32)
+    assert np.array_equal(mb, pop(oracle.puttables(b, w, 1))) and np.array_equal(mw, pop(oracle.puttables(b, w, 2)))

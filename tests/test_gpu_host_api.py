@@ -84,3 +84,63 @@ def test_playout_host_chunked_pipeline_equals_one_launch(ctx):
     assert L.othello_ctx_trajectory(ctx, ctypes.byref(tbp), ctypes.byref(twp), ctypes.byref(tmp), ctypes.byref(stride),
                                     ctypes.byref(tmax)) == 0
     assert stride.value == n and tmax.value == 120 and tbp.value
+
+
+def test_playout_totals_match_per_game_results():
+    """othello_playout_args.totals = what play_a_game reports per game, summed over the launch"""
+    w = torch.from_numpy(np.tile(np.arange(10, dtype=np.float32) - 3, (4, 1)).copy()).to(DEV)
+    for kw in (dict(n_games=5000 + 13), dict(n_games=3000 + 5, policy=ops.POLICY_GREEDY, random_plies=6, weights=w)):
+        tot = torch.zeros(4, dtype=torch.int64, device=DEV)
+        po = ops.playout(seed=9, gid0=77, device=DEV, trajectory=False, totals=tot, **kw)
+        c = po.final_counts().cpu().numpy().astype(np.int64)
+        want = [int(po.nplies.sum()), int((c[:, 0] - c[:, 1]).sum()), int((c[:, 0] > c[:, 1]).sum()),
+                int((c[:, 1] > c[:, 0]).sum())]
+        assert tot.cpu().tolist() == want
+        ops.playout(seed=9, gid0=77, device=DEV, trajectory=False, totals=tot, **kw)     # += semantics
+        assert tot.cpu().tolist() == [2 * v for v in want]
+
+
+def test_playout_host_async_two_batches_in_flight(ctx):
+    """issue batch i+1 before waiting for batch i; every batch must equal the single-launch path and its
+    totals the sums of its per-game results; outputs may be left out (NULL) individually"""
+    L = _lib.lib()
+    n = 200000 + 3
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    bufs = [(pin(n, torch.int32), pin(n, torch.int64), pin(n, torch.int64), pin(4, torch.int64)) for _ in range(2)]
+    T = lambda t: ctypes.c_void_p(t.data_ptr())
+    b0 = pin(n, torch.int64).fill_(ops.signed64(ops.START_BLACK))
+    w0 = pin(n, torch.int64).fill_(ops.signed64(ops.START_WHITE))
+    tickets = [0, 0]
+    steps = 5
+    for i in range(steps + 1):
+        if i < steps:
+            o = bufs[i % 2]
+            tk = ctypes.c_int64()
+            up = (T(b0), T(w0)) if i % 2 else (None, None)        # with and without uploaded start positions
+            assert L.othello_playout_host_async(ctx, 21, 1000 * i, n, up[0], up[1], None, 0, 0, 0, 0, None, -1, None, 120,
+                                                None, None, None, T(o[0]), T(o[1]), T(o[2]), T(o[3]), ctypes.byref(tk)) == 0
+            assert tk.value > 0
+            tickets[i % 2] = tk.value
+        if i > 0:
+            j = i - 1
+            assert L.othello_ctx_wait(ctx, tickets[j % 2]) == 0
+            o = bufs[j % 2]
+            po = ops.playout(n, seed=21, gid0=1000 * j, device=DEV, trajectory=False)
+            assert torch.equal(o[0], po.nplies.cpu()) and torch.equal(o[1], po.final_black.cpu())
+            assert torch.equal(o[2], po.final_white.cpu())
+            c = po.final_counts().cpu().numpy().astype(np.int64)
+            assert o[3].tolist() == [int(po.nplies.sum()), int((c[:, 0] - c[:, 1]).sum()),
+                                     int((c[:, 0] > c[:, 1]).sum()), int((c[:, 1] > c[:, 0]).sum())]
+    assert L.othello_ctx_wait(ctx, tickets[0]) == 0 and L.othello_ctx_wait(ctx, 0) == 0      # waiting twice is harmless
+    assert L.othello_ctx_wait(ctx, 10 ** 9) == -1                                            # a ticket never issued
+    # totals only
+    tot = pin(4, torch.int64)
+    tk = ctypes.c_int64()
+    assert L.othello_playout_host_async(ctx, 21, 0, n, None, None, None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
+                                        None, None, None, T(tot), ctypes.byref(tk)) == 0
+    assert L.othello_ctx_wait(ctx, tk.value) == 0
+    assert int(tot[0]) == int(ops.playout(n, seed=21, gid0=0, device=DEV, trajectory=False).nplies.sum())
+    assert L.othello_ctx_set_option(ctx, 1, 4) == 0 and L.othello_ctx_set_option(ctx, 99, 1) == -1
+    # the synchronous small-batch calls still work while nothing is pending, and after a playout
+    own = np.array([ops.START_BLACK], np.uint64); opp = np.array([ops.START_WHITE], np.uint64); out = np.zeros(1, np.uint64)
+    assert L.othello_legal_host(ctx, P(own), P(opp), P(out), 1) == 0 and int(out[0]) == 0x0000102004080000

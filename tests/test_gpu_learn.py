@@ -35,23 +35,27 @@ def expected_stats(oracle, po_ref, lam=0.90):
 def test_learn_statistics_match_numpy(oracle):
     n = 300
     po = ops.playout(n, seed=4, gid0=0, device=DEV)
-    got = ops.learn_accumulate(po).cpu().numpy()
+    acc = ops.learn_accumulate(po)
+    got = ops.learn_stats(acc).cpu().numpy()
     want = expected_stats(oracle, oracle.playout(4, 0, n))
     assert np.array_equal(got[:, :100], want[:, :100])                 # integer sums: exact
     assert np.array_equal(got[:, 110], want[:, 110])
     assert np.allclose(got[:, 100:110], want[:, 100:110], rtol=1e-9, atol=1e-9)
     assert np.allclose(got[:, 111], want[:, 111], rtol=1e-9)
     assert got[:, 110].sum() == 2 * (po.total_positions() + n)
+    assert np.array_equal(got[:, 109], np.zeros(4))                      # Xty[intercept]: Black's and White's targets cancel
+    from subproc_b200 import learner
+    assert np.array_equal(learner.stats_from_acc(acc.cpu()), got)        # host and device read the integers alike
 
 
 def test_learn_statistics_are_additive_over_shards_of_games():
     """the multi-GPU contract: stats(all games) == sum of stats(shards) (what the all-reduce does)"""
-    whole = ops.learn_accumulate(ops.playout(4096, seed=8, gid0=0, device=DEV))
+    whole = ops.learn_accumulate(ops.playout(4096 + 77, seed=8, gid0=0, device=DEV))
     parts = torch.zeros_like(whole)
-    for k in range(4):
-        ops.learn_accumulate(ops.playout(1024, seed=8, gid0=1024 * k, device=DEV), stats=parts)
-    assert torch.equal(whole[:, :100], parts[:, :100])
-    assert torch.allclose(whole, parts, rtol=1e-9, atol=1e-9)
+    for lo, hi in ((0, 1000), (1000, 1031), (1031, 3000), (3000, 4096 + 77)):        # ragged shards
+        ops.learn_accumulate(ops.playout(hi - lo, seed=8, gid0=lo, device=DEV), acc=parts)
+    assert torch.equal(whole, parts)                                   # integer accumulators: bit-identical
+    assert torch.equal(ops.learn_stats(whole), ops.learn_stats(parts))
 
 
 def test_device_solve_matches_host_solve():
@@ -63,7 +67,7 @@ def test_device_solve_matches_host_solve():
         po = ops.playout(n, seed=14, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, random_plies=8, weights=w0, t_max=t_max)
         if t_max < 120:
             po.nplies.clamp_(max=t_max)                               # treat the truncated prefix as whole games
-        stats = ops.learn_accumulate(po)
+        stats = ops.learn_stats(ops.learn_accumulate(po))
         w, params, fits = ops.learn_solve(stats, w0)
         host = learner.fit_from_stats(stats)
         f = fits.cpu().numpy()

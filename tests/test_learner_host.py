@@ -156,3 +156,66 @@ def test_batch_stats_payload_follows_the_reference_loop():
     assert got['min_disc_diff'] == min(diff) and got['max_disc_diff'] == max(diff)
     assert got['avg_disc_diff'] == float(sum(diff)) / 300 and got['diffs'] == sorted(diff) and got['params_used'] == 'p'
     assert got['white_wins_by_discs'] == int((w > b).sum())
+
+
+def acc_from_samples(x9, y, discs):
+    """the exact integer accumulators of othello_learn_accumulate (include/othello_b200.h) in numpy /
+    Python integers, every sample handed over as its own 2^-40 fixed-point partial sum"""
+    acc = np.zeros((4, learner.N_ACC), dtype=np.int64)
+    x = np.concatenate([x9, np.ones((x9.shape[0], 1))], axis=1).astype(np.int64)
+    for s, (lo, hi) in enumerate(learner.PHASE_SHARDS):
+        m = (discs >= lo) & (discs <= hi)
+        g = x[m].T @ x[m]
+        for i in range(10):
+            for j in range(i, 10):
+                acc[s, learner._pair(i, j)] = g[i, j]
+        for k in range(10):
+            vals = (x[m][:, k] * y[m]) if k < 9 else (y[m] * y[m])
+            q = sum(int(round(float(v) * 2.0 ** 40)) for v in vals)
+            acc[s, 56 + 2 * k], acc[s, 57 + 2 * k] = q >> 32, q & 0xFFFFFFFF
+    return acc
+
+
+def test_stats_from_acc_reads_the_integers_exactly():
+    x9, y, discs = synthetic(3000, 5)
+    y = np.round(y * 64) / 64                                     # dyadic targets: the fixed point holds them exactly
+    got = learner.stats_from_acc(acc_from_samples(x9, y, discs))
+    want = stats_from_samples(x9, y, discs)
+    assert np.array_equal(got[:, :100], want[:, :100]) and np.array_equal(got[:, 110], want[:, 110])
+    assert np.allclose(got[:, 100:109], want[:, 100:109], rtol=1e-13) and np.allclose(got[:, 111], want[:, 111], rtol=1e-13)
+    assert np.array_equal(got[:, 109], np.zeros(4))               # the kernel never accumulates Xty[intercept]
+
+
+def _acc_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x9, y, discs = synthetic(6000, 4)
+    lo, hi = learner.shard_of_games(6000, rank, world)
+    L = learner.ProgressPositionMovesLearn()
+    L.learn_from_acc(torch.from_numpy(acc_from_samples(x9[lo:hi], y[lo:hi], discs[lo:hi])))
+    q.put((rank, L.read_parameters(), [f['coef'].tolist() for f in L.last_fits]))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_allreduce_of_integer_accumulators_is_exact():
+    """the N > 1 learner path over gloo: all-reduce of the int64 accumulators, then the same bits as one process"""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_acc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x9, y, discs = synthetic(6000, 4)
+    L = learner.ProgressPositionMovesLearn()
+    L.learn_from_acc(torch.from_numpy(acc_from_samples(x9, y, discs)))
+    for rank, params, coefs in got:
+        assert params == L.read_parameters()                       # == , not a tolerance
+        assert coefs == [f['coef'].tolist() for f in L.last_fits]

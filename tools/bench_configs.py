@@ -8,7 +8,7 @@
 selfplay (config 4): every rank plays `games` greedy self-play games per step (first 10 plies uniformly
 random, then arg-max of the linear evaluation on the default_value() rows), trajectories to HBM.
 learner (config 5): per step = one learning iteration: greedy self-play with the current weights,
-othello_learn_accumulate, ONE all-reduce of 4x112 doubles over NCCL, four 10x10 solves, +-127 scaling,
+othello_learn_accumulate, ONE all-reduce of 4x80 int64 accumulators over NCCL, four 10x10 solves, +-127 scaling,
 int() truncation.  Timing: CUDA events, max over ranks; rank 0 prints one JSON line.
 """
 import argparse
@@ -67,11 +67,12 @@ def main():
         w = torch.from_numpy(L.weights_table()).to(dev)
         ops.playout(G, seed=2, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY, random_plies=args.random_plies,
                     weights=w, out=po)
-        stats = L.accumulate(po)
+        acc = L.accumulate(po)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        learner.allreduce_stats(stats)
+        learner.allreduce_stats(acc)                         # 320 int64: exact sums
         e1.record()
+        stats = ops.learn_stats(acc)
         L.last_stats = stats
         L.last_fits = learner.fit_from_stats(stats)          # D2H of 3.6 KB + four 10x10 solves on the host
         rows = [learner.scale_param(f['coef']) if f['n'] else tuple(L.read_parameters()[1 + 9 * s:10 + 9 * s])
