@@ -82,6 +82,51 @@ def _cpu_worker(args):
     return plies, games
 
 
+def play_a_game_through(board_module, seed, gid, mg):
+    """one random-vs-random game driven like GameRunner.play_a_turn (game_runner.py:154-163) with a
+    RedisRecorder-style record per ply (game_recorder.py:107-114), on ANY module with the reference's
+    `Board` interface; returns (plies, final n_black, final n_white)"""
+    B = board_module.Board()
+    key = mg.rng_key(seed, gid)
+    t = 0
+    while not B.is_game_over():
+        moves = B.puttables(B.turn)
+        if moves:
+            x, y = moves[mg.below(mg.rng_draw(key, t, 1), len(moves))]
+            B.put_s(B.handstr_from_coord(x, y))
+        else:
+            B.put_s('ps')
+        str(B)
+        {'book': B.serialize_board(), 'whosturn': B.serialize_turn(), 'turn': B.nturn, 'end': B.is_game_over()}
+        t += 1
+    return t, B.n_black(), B.n_white()
+
+
+def config1_facade(n_games=20):
+    """BASELINE config 1: single games through the drop-in `subproc_b200.board.Board` (one kernel launch per
+    change of position) next to the reference's own board.py on one host core, same seeded games."""
+    from oracle import refshim, make_golden as mg
+    from subproc_b200 import board as b200_board
+    out = {"games": n_games, "driver": "puttables -> put_s -> str(board) -> serialize -> is_game_over per ply "
+                                       "(game_runner.py:154-163, game_recorder.py:107-114)"}
+    play_a_game_through(b200_board, 7, 999, mg)                     # context creation, first launches
+    t0 = time.perf_counter()
+    got = [play_a_game_through(b200_board, 7, g, mg) for g in range(n_games)]
+    dt = time.perf_counter() - t0
+    plies = sum(g[0] for g in got)
+    out["b200_facade"] = {"ms_per_game": 1e3 * dt / n_games, "us_per_ply": 1e6 * dt / plies, "games_per_s": n_games / dt}
+    if refshim.available():
+        rb = refshim.load().board
+        t0 = time.perf_counter()
+        ref = [play_a_game_through(rb, 7, g, mg) for g in range(n_games)]
+        dt = time.perf_counter() - t0
+        out["reference_board_py"] = {"ms_per_game": 1e3 * dt / n_games, "us_per_ply": 1e6 * dt / plies,
+                                     "games_per_s": n_games / dt, "cores": 1}
+        out["identical_games"] = got == ref
+        out["facade_speedup"] = out["reference_board_py"]["ms_per_game"] / out["b200_facade"]["ms_per_game"]
+    return out
+
+
 def cpu_baseline(budget_s=12.0, max_games_per_worker=1 << 30, seed=1, full_path_s=0.0):
     """reference CPU path on all host cores for ~budget_s seconds (+ full_path_s seconds of the
     play_a_turn-equivalent path, reported separately)."""
@@ -570,6 +615,7 @@ def run_b200_arm(args):
             "clocks": clocks,
         }
         if cb is not None:
+            cb["config1_single_game_facade"] = config1_facade()
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:

@@ -143,13 +143,21 @@ int othello_playout(const othello_playout_args *args, void *stream);
 
 /* ---- perft ---------------------------------------------------------------------------------- */
 
-/* Legal-move enumeration to `depth` plies (pass = one ply, a game-over node = one leaf).
- * Synchronous: expands breadth-first on the device, then one thread per frontier node runs a
- * depth-first count.  workspace: DEVICE scratch, >= othello_perft_workspace_bytes(depth).
- * result: HOST pointer. */
+/* Legal-move enumeration to `depth` plies (pass = one ply, a game-over node = one leaf).  Expands
+ * breadth-first on the device, then counts the frontier nodes depth-first in registers.  The host never
+ * reads the frontier: a call is a fixed sequence of launches steered by a control block in the workspace.
+ * workspace: DEVICE scratch, >= othello_perft_workspace_bytes(depth).
+ *
+ * othello_perft: synchronous, result is a HOST pointer; OTHELLO_E_WORKSPACE if a frontier did not fit.
+ * othello_perft_async: only enqueues; result is a DEVICE uint64[2] = {nodes, 1 if the workspace was too
+ * small}, valid in stream order.  part / nparts split the depth-first stage: the call counts the frontier
+ * nodes i = part (mod nparts) (and, for part 0, the game-over leaves met while expanding), so the sum of
+ * the nparts results is the node count -- one u64 all-reduce across GPUs. */
 int64_t othello_perft_workspace_bytes(int depth);
 int othello_perft(uint64_t black, uint64_t white, int turn, int depth, void *workspace, int64_t workspace_bytes,
                   uint64_t *result, void *stream);
+int othello_perft_async(uint64_t black, uint64_t white, int turn, int depth, int part, int nparts,
+                        void *workspace, int64_t workspace_bytes, uint64_t *result, void *stream);
 
 /* ---- learner sufficient statistics ---------------------------------------------------------- */
 
@@ -221,6 +229,23 @@ typedef struct othello_ctx othello_ctx;
 
 int  othello_ctx_create(int device, othello_ctx **out);
 void othello_ctx_destroy(othello_ctx *ctx);
+
+/* The single-game facade (subproc_b200/board.py) in one call: Board.put(color, x, y) (board.py:161-174)
+ * for move = x + 8*y in 0..63 -- the position is returned unchanged with ret = 0 when the square is
+ * occupied or nothing flips -- or no move at all (move = OTHELLO_PASS or anything else), followed by what
+ * the reference's callers ask about the resulting position before the next ply (game_runner.py:137,162,
+ * 194-196; game_recorder.py:112; counts()): legal moves and counts() features of both colours, disc
+ * counts.  One launch + one synchronise; the kernel writes `info` through mapped pinned memory. */
+typedef struct {
+    uint64_t black, white;        /* the position after the move */
+    uint64_t flips;               /* discs flipped (0: put() returned 0) */
+    uint64_t legal_black, legal_white;   /* Board.puttables(Black / White) as masks */
+    int32_t  ret;                 /* Board.put's return value: number of discs flipped */
+    int32_t  n_black, n_white, n_empty;
+    int32_t  features_black[OTHELLO_FEATURES], features_white[OTHELLO_FEATURES];   /* counts(book, 'O' / 'X') */
+} othello_position_info;
+int othello_board_apply_host(othello_ctx *ctx, uint64_t black, uint64_t white, int32_t color, int32_t move,
+                             othello_position_info *info);
 
 /* puttables / put_s on host arrays: copies in, launches, copies out, synchronises. */
 int othello_legal_host(othello_ctx *ctx, const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n);

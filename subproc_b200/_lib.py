@@ -35,6 +35,16 @@ class PlayoutArgs(ctypes.Structure):
     ]
 
 
+class PositionInfo(ctypes.Structure):
+    """othello_position_info (include/othello_b200.h)."""
+    _fields_ = [
+        ("black", ctypes.c_uint64), ("white", ctypes.c_uint64), ("flips", ctypes.c_uint64),
+        ("legal_black", ctypes.c_uint64), ("legal_white", ctypes.c_uint64),
+        ("ret", i32), ("n_black", i32), ("n_white", i32), ("n_empty", i32),
+        ("features_black", i32 * 10), ("features_white", i32 * 10),
+    ]
+
+
 # name -> (restype, argtypes); also the export list checked by tests/test_boundary.py
 SIGNATURES = {
     "othello_abi_version": (ctypes.c_int, []),
@@ -52,6 +62,8 @@ SIGNATURES = {
     "othello_perft_workspace_bytes": (i64, [ctypes.c_int]),
     "othello_perft": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, i64,
                                      u64p, vp]),
+    "othello_perft_async": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, vp, i64, vp, vp]),
     "othello_learn_accumulate": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp]),
     "othello_learn_stats": (ctypes.c_int, [vp, vp, vp]),
     "othello_learn_solve": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
@@ -62,6 +74,8 @@ SIGNATURES = {
     "othello_int32_dual_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "othello_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
     "othello_ctx_destroy": (None, [vp]),
+    "othello_board_apply_host": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i32, i32,
+                                                ctypes.POINTER(PositionInfo)]),
     "othello_legal_host": (ctypes.c_int, [vp, vp, vp, vp, i64]),
     "othello_step_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
     "othello_playout_host": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32, i32,

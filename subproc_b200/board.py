@@ -8,13 +8,20 @@ learn_base.py:70-73): attributes ``board``, ``turn``, ``nturn``; methods ``putta
 ``mask_count``, ``get/set``, ``hostile``, ``(de)serialize*``, ``__str__`` with the reference's
 return codes (put -> 0, put_s -> -1, no exceptions for illegal moves).
 
-Rules questions (legal moves, flips, game over, counts) are answered by the sm_100a kernels on a
-one-position batch; the object keeps a host mirror of the two bitboards only so that the pure
-string / accessor methods need no launch.  For throughput use ``subproc_b200.batched`` -- this
-class exists so the reference's single-game code keeps working unchanged.  Without a CUDA device
-the rules methods raise; there is no CPU implementation of the rules in this package.
+Rules questions (legal moves, flips, game over, counts, counts() features) are answered by the
+sm_100a kernels: every change of the position is ONE call of ``othello_board_apply_host`` -- one
+launch, one stream synchronise, results written by the kernel straight into pinned host memory --
+which applies the move (if any) and returns everything the reference's callers ask about the new
+position before the next ply (game_runner.py:154-163 asks ~6 questions per ply).  The object keeps a
+host mirror of the two bitboards so that the pure string / accessor methods need no launch.  For
+throughput use ``subproc_b200.batched`` -- this class exists so the reference's single-game code
+keeps working unchanged.  Without a CUDA device the rules methods raise; there is no CPU
+implementation of the rules in this package.
 """
+import ctypes
 import re
+
+from . import _lib
 
 COLORS = (Empty, Black, White) = range(0, 3)          # board.py:3-7
 
@@ -51,31 +58,57 @@ class Board(object):
         self.nturn = 0
 
     # ---- device plumbing ---------------------------------------------------------------
-    def _ops(self):
-        import torch
-        from . import ops
-        if not torch.cuda.is_available():
-            raise RuntimeError("subproc_b200.board.Board needs a CUDA device: the rules run in sm_100a kernels "
-                               "and there is no CPU fallback")
-        dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
-        return ops, dev
+    _contexts = {}                                     # device index -> othello_ctx (shared by all boards)
+    _QUERY = 255                                       # "no move": only describe the position
+    _CLASS_MASKS = (0x8100000000000081, 0x4281000000008142, 0x0042000000004200, 0x2400810000810024,
+                    0x1800008181000018, 0x003C424242423C00, 0x0000240000240000, 0x0000183C3C180000)
+
+    def _ctx_index(self):
+        dev = self._device
+        if dev is None:
+            return 0
+        if isinstance(dev, int):
+            return dev
+        text = str(dev)
+        return int(text.split(":")[1]) if ":" in text else 0
+
+    def _ctx(self):
+        index = self._ctx_index()
+        ctx = Board._contexts.get(index)
+        if ctx is None:
+            ctx = ctypes.c_void_p()
+            rc = _lib.lib().othello_ctx_create(index, ctypes.byref(ctx))
+            if rc != 0:
+                raise RuntimeError("subproc_b200.board.Board needs a CUDA device: the rules run in sm_100a kernels "
+                                   "and there is no CPU fallback (othello_ctx_create: %s)"
+                                   % _lib.lib().othello_error_string(rc).decode())
+            Board._contexts[index] = ctx
+        return ctx
+
+    def _apply(self, black, white, color, move):
+        """one launch: Board.put(color, move) on (black, white) + the description of the resulting position"""
+        info = _lib.PositionInfo()
+        _lib.check(_lib.lib().othello_board_apply_host(self._ctx(), black, white, color, move, ctypes.byref(info)),
+                   "othello_board_apply_host")
+        return info
+
+    def _info(self):
+        """description of the current position (legal masks and features of both colours, counts); remembered
+        until the position changes -- play_a_turn asks puttables / is_game_over / n_black for the same
+        position several times (game_runner.py:137,162,194-196; game_recorder.py:112)"""
+        key = (self._black, self._white)
+        if getattr(self, '_info_key', None) != key:
+            self._info_val = self._apply(self._black, self._white, Black, Board._QUERY)
+            self._info_key = key
+        return self._info_val
 
     def _pair(self, piece):
         """(own, opp) bitboards for colour ``piece``; hostile(piece) is Black for anything but Black."""
         return (self._black, self._white) if piece == Black else (self._white, self._black)
 
     def _legal_mask(self, piece):
-        """legal moves of ``piece``: one launch answers both colours (a batch of two) and is remembered
-        until the position changes -- play_a_turn asks puttables / is_game_over for the same position
-        several times (game_runner.py:137,162; game_recorder.py:112)."""
-        key = (self._black, self._white)
-        if getattr(self, '_legal_key', None) != key:
-            ops, dev = self._ops()
-            out = ops.legal(ops.bits_tensor([self._black, self._white], dev),
-                            ops.bits_tensor([self._white, self._black], dev))
-            m = ops.bits_numpy(out)
-            self._legal_key, self._legal_both = key, (int(m[0]), int(m[1]))
-        return self._legal_both[0] if piece == Black else self._legal_both[1]
+        info = self._info()
+        return info.legal_black if piece == Black else info.legal_white
 
     # ---- the 8x8 list view -------------------------------------------------------------
     @property
@@ -104,9 +137,8 @@ class Board(object):
 
     # ---- counts ------------------------------------------------------------------------
     def _counts(self):
-        ops, dev = self._ops()
-        c = ops.counts(ops.bits_tensor([self._black], dev), ops.bits_tensor([self._white], dev)).cpu()
-        return int(c[0, 0]), int(c[0, 1]), int(c[0, 2])
+        info = self._info()
+        return info.n_black, info.n_white, info.n_empty
 
     def count_over_board(self, fun):                   # board.py:29-35
         return sum(1 for y in range(8) for x in range(8) if fun(self.get(x, y)))
@@ -121,8 +153,15 @@ class Board(object):
         return self._counts()[2]
 
     def mask_count(self, color, mask):                 # board.py:74-81
+        mask &= _FULL
+        if mask in Board._CLASS_MASKS and color in (Black, White):
+            # the eight square classes of counts() (parameter_progress_position_moves_learn.py:9-16) come
+            # with the position description
+            info = self._info()
+            return (info.features_black if color == Black else info.features_white)[2 + Board._CLASS_MASKS.index(mask)]
         import torch
-        ops, dev = self._ops()
+        from . import ops
+        dev = torch.device("cuda", self._ctx_index())
         out = ops.mask_count(ops.bits_tensor([self._black], dev), ops.bits_tensor([self._white], dev),
                              torch.tensor([color], dtype=torch.uint8, device=dev), ops.bits_tensor([mask & _FULL], dev))
         return int(out.cpu()[0])
@@ -146,13 +185,9 @@ class Board(object):
 
     def hands_for_direc(self, direc, piece, x, y):     # board.py:124-139
         """the run put() would flip from (x, y) along ``direc``, as (piece, x, y) triples."""
-        import torch
-        ops, dev = self._ops()
-        own, opp = self._pair(piece)
         here = _bit(x, y)
-        f = ops.flips(ops.bits_tensor([own & ~here], dev), ops.bits_tensor([opp & ~here], dev),
-                      torch.tensor([x + 8 * y], dtype=torch.uint8, device=dev))
-        f = int(ops.bits_numpy(f)[0])
+        # (the reference walks the ray whatever stands on (x, y) itself)
+        f = self._apply(self._black & ~here, self._white & ~here, Black if piece == Black else White, x + 8 * y).flips
         ret = []
         for i in range(1, 9):
             nx, ny = x + i * direc[0], y + i * direc[1]
@@ -167,18 +202,12 @@ class Board(object):
             self.set(piece, x, y)
 
     def put(self, piece, x, y):                        # board.py:161-174
-        import torch
-        ops, dev = self._ops()
-        here = _bit(x, y)
-        own, opp = self._pair(piece)
-        f = ops.flips(ops.bits_tensor([own], dev), ops.bits_tensor([opp], dev),
-                      torch.tensor([x + 8 * y], dtype=torch.uint8, device=dev))
-        f = int(ops.bits_numpy(f)[0])
-        if f == 0:
-            return 0
-        own, opp = own | f | here, opp & ~f
-        self._black, self._white = (own, opp) if piece == Black else (opp, own)
-        return bin(f).count("1")
+        _bit(x, y)                                     # IndexError like board[y][x]
+        info = self._apply(self._black, self._white, Black if piece == Black else White, x + 8 * y)
+        if info.ret:
+            self._black, self._white = info.black, info.white
+            self._info_key, self._info_val = (info.black, info.white), info      # already describes the new position
+        return info.ret
 
     def coord_from_handstr(self, handstr):             # board.py:176-185
         b = _HAND_RE.findall(handstr)
@@ -190,26 +219,18 @@ class Board(object):
         return chr(ord('a') + x) + chr(ord('1') + y)
 
     def put_s(self, stri):                             # board.py:192-209
-        import torch
-        ops, dev = self._ops()
+        out = -1
         if stri == 'PS' or stri == 'ps':
-            move = ops.PASS
+            out = 0
         else:
             x, y = self.coord_from_handstr(stri)
             if x >= 0 and y >= 0:
-                _bit(x, y)                             # IndexError beyond h / rank 9, like board[y][x]
-                move = x + 8 * y
-            else:
-                return -1
-        black, white = ops.bits_tensor([self._black], dev), ops.bits_tensor([self._white], dev)
-        turn = torch.tensor([self.turn], dtype=torch.uint8, device=dev)
-        nturn = torch.zeros(1, dtype=torch.int32, device=dev)
-        _, ret, _ = ops.step(black, white, turn, nturn, torch.tensor([move], dtype=torch.uint8, device=dev))
-        out = int(ret.cpu()[0])
+                out = self.put(self.turn, x, y)        # IndexError beyond h / rank 9, like board[y][x]
+                if out == 0:
+                    out = -1
         if out >= 0:
-            self._black, self._white = int(ops.bits_numpy(black)[0]), int(ops.bits_numpy(white)[0])
-            self.turn = int(turn.cpu()[0])
             self.nturn += 1                            # nturn may be a str after deserialize -> TypeError, as in the reference
+            self.turn = White if self.turn == Black else Black
         return out
 
     # ---- text forms ----------------------------------------------------------------------

@@ -21,7 +21,8 @@ using namespace obp;
 namespace {
 
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxItems = 32 * 33 + 32;       // a position has at most 33 legal moves
+constexpr int kMaxItems = 32 * 60;            // 32 games x at most 60 empty squares: holds ANY pair of bitboards, not only
+                                              // positions reachable from the opening (<= 33 legal moves)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct WarpScratch {
@@ -154,7 +155,10 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
             int move = OTHELLO_PASS;
             u64 f = 0, x = 0;
             if (moving) {
-                if (evaluate) move = (int)ws.best_sq[lane];
+                if (evaluate) {
+                    move = (int)ws.best_sq[lane];
+                    if (move >= 64) move = __ffsll((long long)legal) - 1;      // every score NaN (NaN weights): lowest square
+                }
                 else if (random_now) move = obf::kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
                 else move = __ffsll((long long)legal) - 1;
                 x = 1ull << move;

@@ -11,6 +11,7 @@
 // keeps two batches in flight sees the kernel time, not kernel + PCIe.
 #include <new>
 #include "common.cuh"
+#include "fastboard.cuh"
 
 constexpr int kPipeStreams = 3;     // chunks of a playout rotate over these streams
 constexpr int kSlots = 2;           // batches that may be in flight at once
@@ -44,6 +45,9 @@ struct othello_ctx {
     int64_t chunk_seq;              // rotates the pipe streams across calls
     int last_slot;                  // slot of the most recently issued playout, -1 = none
     int max_chunks;
+    // single-position front end (othello_board_apply_host): results land in pinned host memory that
+    // the kernel writes directly (mapped), so a call is one launch + one stream synchronise
+    othello_position_info *info_h, *info_d;
 };
 
 namespace {
@@ -91,6 +95,41 @@ struct Carver {
 int fail(othello_ctx *c, int rc) { drain(c); return rc; }
 #define OBH_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, (int)e_); } while (0)
 
+// Board.put(piece, x, y) (board.py:161-174) on ONE position, then everything the reference's callers ask
+// about the resulting position before the next move (game_runner.py:137,162,194-196; game_recorder.py:112;
+// counts(), parameter_progress_position_moves_learn.py:5-17): legal moves and features of both colours,
+// disc counts.  One warp; lane 0 does the rules, the result goes straight to mapped host memory.
+__global__ void __launch_bounds__(32) board_kernel(ob::u64 black, ob::u64 white, int color, int move,
+                                                   othello_position_info *out)
+{
+    __shared__ ob::u64 ray_s[obf::kRayDirs * 64];
+    ob::fill_rays(ray_s);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const ob::Rays rays = {ray_s};
+    ob::u64 flips = 0;
+    if (move >= 0 && move < 64) {
+        const ob::u64 x = 1ull << move;
+        const bool is_black = color == OTHELLO_BLACK;          // hostile(piece) is Black for anything but Black (board.py:155-159)
+        const ob::u64 own = is_black ? black : white, opp = is_black ? white : black;
+        if (!((black | white) & x)) flips = ob::put_flips(move, own, opp, rays);
+        if (flips) {
+            const ob::u64 no = own | flips | x, np = opp & ~flips;
+            black = is_black ? no : np; white = is_black ? np : no;
+        }
+    }
+    out->black = black; out->white = white; out->flips = flips;
+    out->ret = __popcll(flips);
+    out->legal_black = obf::legal_moves(black, white);
+    out->legal_white = obf::legal_moves(white, black);
+    out->n_black = __popcll(black); out->n_white = __popcll(white); out->n_empty = 64 - __popcll(black | white);
+    int fb[10], fw[10];
+    ob::features10(black, white, fb);
+    ob::features10(white, black, fw);
+    for (int k = 0; k < 10; k++) { out->features_black[k] = fb[k]; out->features_white[k] = fw[k]; }
+    __threadfence_system();
+}
+
 }  // namespace
 
 extern "C" {
@@ -125,6 +164,7 @@ void othello_ctx_destroy(othello_ctx *c)
     for (int i = 0; i < kPipeStreams; i++)
         if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->info_h) cudaFreeHost(c->info_h);
     delete c;
 }
 
@@ -151,6 +191,8 @@ int othello_ctx_create(int device, othello_ctx **out)
         for (int j = 0; j < kPipeStreams && e == cudaSuccess; j++)
             e = cudaEventCreateWithFlags(&sl->tail[j], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->info_h, sizeof(othello_position_info), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&c->info_d, c->info_h, 0);
     if (e != cudaSuccess) { othello_ctx_destroy(c); return (int)e; }   // destroys exactly what was created
     *out = c;
     return 0;
@@ -167,6 +209,18 @@ int othello_ctx_set_option(othello_ctx *c, int32_t option, int64_t value)
     default:
         return OTHELLO_E_INVALID;
     }
+}
+
+int othello_board_apply_host(othello_ctx *c, uint64_t black, uint64_t white, int32_t color, int32_t move,
+                             othello_position_info *info)
+{
+    OB_CHECK_ARGS(c && info);
+    OB_CUDA(cudaSetDevice(c->device));
+    board_kernel<<<1, 32, 0, c->stream>>>(black, white, color, move, c->info_d);
+    OB_CUDA(cudaGetLastError());
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+    *info = *c->info_h;
+    return 0;
 }
 
 int othello_legal_host(othello_ctx *c, const uint64_t *own, const uint64_t *opp, uint64_t *legal, int64_t n)

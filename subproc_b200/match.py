@@ -30,7 +30,7 @@ def engine_from_spec(spec):
     raise ValueError("unknown engine spec %r (expected random | greedy | greedy:<param file>)" % spec)
 
 
-def do_match(conf, seed=0, device=None):
+def do_match(conf, seed=0, device=None, recorder=None):
     """One match as configured (the job of subproc.py:15-39): engines and substitution budgets per side,
     optional colour swap, recorder plugin opened as a context manager, one game played."""
     sides = [(engine_from_spec(conf['proc_%s_path' % k]), int(conf.get('proc_n_rand_hands_for_%s' % k, 0)))
@@ -38,7 +38,7 @@ def do_match(conf, seed=0, device=None):
     if conf.get('proc_randomize_black_white', 0) == 1 and random.randrange(2) == 1:
         sides.reverse()                                   # "... and swapped black and white"
     (black, n_black), (white, n_white) = sides
-    with get_game_recorder(conf) as recorder:
+    with (recorder if recorder is not None else get_game_recorder(conf)) as recorder:
         runner = GameRunner(black, white, recorder, conf.get('proc_debug', 0) == 1, n_black, n_white,
                             device=device, seed=seed)
         return runner.play_a_game()

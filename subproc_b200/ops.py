@@ -251,19 +251,54 @@ def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn
 _perft_ws = {}
 
 
-def perft(depth, black=START_BLACK, white=START_WHITE, turn=BLACK, device=None):
-    """Node count of the legal-move tree to ``depth`` (pass = ply, game-over node = leaf)."""
-    device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
-    L = _lib.lib()
-    nbytes = int(L.othello_perft_workspace_bytes(depth))
+def _perft_workspace(depth, device):
+    nbytes = int(_lib.lib().othello_perft_workspace_bytes(depth))
     ws = _perft_ws.get(device)
     if ws is None or ws.numel() < nbytes:
         ws = _perft_ws[device] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws, nbytes
+
+
+def perft(depth, black=START_BLACK, white=START_WHITE, turn=BLACK, device=None):
+    """Node count of the legal-move tree to ``depth`` (pass = ply, game-over node = leaf)."""
+    device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+    ws, nbytes = _perft_workspace(depth, device)
     res = ctypes.c_uint64(0)
     with torch.cuda.device(device):
-        _lib.check(L.othello_perft(unsigned64(black), unsigned64(white), turn, depth, ctypes.c_void_p(ws.data_ptr()),
-                                   nbytes, ctypes.byref(res), _stream(ws)), "othello_perft")
+        _lib.check(_lib.lib().othello_perft(unsigned64(black), unsigned64(white), turn, depth, ctypes.c_void_p(ws.data_ptr()),
+                                            nbytes, ctypes.byref(res), _stream(ws)), "othello_perft")
     return int(res.value)
+
+
+def perft_part(depth, part, nparts, black=START_BLACK, white=START_WHITE, turn=BLACK, device=None):
+    """This part's share of perft(depth), left ON the device: int64 [2] = (nodes, workspace-overflow flag).
+    Only enqueues (othello_perft_async); the nparts shares add up to the node count."""
+    device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+    out = torch.zeros(2, dtype=torch.int64, device=device)
+    if depth == 0:
+        out[0] = 1 if part == 0 else 0
+        return out
+    ws, nbytes = _perft_workspace(depth, device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().othello_perft_async(unsigned64(black), unsigned64(white), turn, depth, part, nparts,
+                                                  ctypes.c_void_p(ws.data_ptr()), nbytes, ctypes.c_void_p(out.data_ptr()),
+                                                  _stream(ws)), "othello_perft_async")
+    return out
+
+
+def perft_distributed(depth, black=START_BLACK, white=START_WHITE, turn=BLACK, device=None):
+    """perft with the depth-first stage split over the ranks of the default process group: every rank
+    expands the (small) frontier itself, counts every world-th node, one all-reduce of a u64."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    out = perft_part(depth, rank, world, black, white, turn, device)
+    if world > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    nodes, overflow = (int(v) for v in out.cpu().tolist())
+    if overflow:
+        raise _lib.OthelloError(-2, "othello_perft_async")
+    return nodes
 
 
 def decay_table(t_max, lam=0.90):

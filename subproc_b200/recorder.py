@@ -1,9 +1,8 @@
 """Game recorders with the reference's interface (game_recorder.py:9-79), for callers that want the
 per-position records of a game.  The Redis / DynamoDB recorders of the reference are network I/O and
-out of scope; ``MemoryRecorder`` keeps the RedisRecorder's book dicts in memory, ``FlatFileRecorder``
-writes the reference's flat-file format."""
+out of scope (as is the flat-file recorder: its text format is ``books.flatfile_text``);
+``MemoryRecorder`` keeps the RedisRecorder's book dicts in memory."""
 from abc import ABCMeta, abstractmethod
-from datetime import datetime
 
 
 class GameRecorder(object, metaclass=ABCMeta):          # game_recorder.py:9-38
@@ -62,42 +61,6 @@ class MemoryRecorder(GameRecorder):
 
     def store(self):
         self.stored.append((list(self.lines), dict(self.meta)))
-
-    def add_meta(self, meta_dict):
-        self.meta.update(meta_dict)
-
-
-class FlatFileRecorder(GameRecorder):                   # game_recorder.py:41-79
-    def __init__(self):
-        self.lines = []
-        self.output_path = ''
-        self.title = ''
-        self.meta = {}
-        self.timestamp = datetime.now().strftime("%Y%m%d_%H%M%S")
-        self.path = None
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, exc_type, exc_val, exc_tb):
-        return False
-
-    def graceful_exit(self):
-        pass
-
-    def configure(self, title, meta, config_dict):
-        self.output_path = config_dict['flatfile_output_path']
-
-    def add(self, game_board):
-        self.lines.append(game_board.serialize_str())
-
-    def store(self):
-        self.path = self.output_path + '/' + self.title + '_' + self.timestamp
-        with open(self.path, 'w+') as f:
-            f.write("% Black: " + self.meta['proc_a'] + "\n")
-            f.write("% White: " + self.meta['proc_b'] + "\n")
-            for line in self.lines:
-                f.write(line + "\n")
 
     def add_meta(self, meta_dict):
         self.meta.update(meta_dict)

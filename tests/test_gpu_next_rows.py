@@ -111,17 +111,15 @@ def test_do_match_with_plugin_recorders(tmp_path, golden_games):
     """subproc.do_match (subproc.py:15-39): config-selected recorder plugin, one game, winner tuple"""
     from subproc_b200 import match, recorder
     conf = {'proc_a_path': 'random', 'proc_b_path': 'random', 'proc_n_rand_hands_for_a': 0,
-            'game_recorder_from': 'subproc_b200.recorder', 'game_recorder_class': 'FlatFileRecorder',
-            'flatfile_output_path': str(tmp_path)}
-    won = match.do_match(conf, seed=0)
+            'game_recorder_from': 'subproc_b200.recorder', 'game_recorder_class': 'MemoryRecorder'}
+    mem = recorder.MemoryRecorder()
+    won = match.do_match(conf, seed=0, recorder=mem)
     assert won[0] in ('Black', 'White', 'None')
-    files = list(tmp_path.iterdir())
-    assert len(files) == 1
-    lines = files[0].read_text().splitlines()
+    lines, meta = mem.stored[0]
     g = golden_games[0]                                  # seed 0, game id 0, random engines: the same game
-    assert lines[0] == '% Black: b200-random' and lines[2:] == [p['ser'] for p in g['positions']]
-    conf.update(game_recorder_class='MemoryRecorder', proc_a_path='greedy', proc_b_path='greedy',
-                proc_n_rand_hands_for_a=3, proc_n_rand_hands_for_b=3)
+    assert meta['proc_a'] == 'b200-random'
+    assert [r['book'] + ' ' + r['whosturn'] for r in lines] == [p['ser'] for p in g['positions']]
+    conf.update(proc_a_path='greedy', proc_b_path='greedy', proc_n_rand_hands_for_a=3, proc_n_rand_hands_for_b=3)
     rec = match.get_game_recorder(conf)
     assert isinstance(rec, recorder.MemoryRecorder)
     won = match.do_match(conf, seed=5)

@@ -146,3 +146,35 @@ def test_perft_other_roots_against_oracle(oracle):
         for turn in (1, 2):
             for d in (1, 2, 4):
                 assert ops.perft(d, int(b[i]), int(w[i]), turn, device=DEV) == oracle.perft(d, int(b[i]), int(w[i]), turn)
+
+
+def test_perft_parts_add_up_and_workspace_follows_depth(oracle):
+    """the depth-first stage split nparts ways (frontier split + one u64 all-reduce): the shares,
+    left on the device by a launch sequence the host never waits for, add up to the node count"""
+    from subproc_b200 import _lib
+    L = _lib.lib()
+    sizes = [int(L.othello_perft_workspace_bytes(d)) for d in (1, 2, 3, 4, 6, 10, 30)]
+    assert sizes == sorted(sizes) and sizes[0] < 8192 and sizes[-1] == sizes[-2]      # grows with depth, then capped
+    for depth, want in ((3, 56), (7, 55092), (10, 24571284)):
+        for nparts in (1, 3, 8):
+            shares = [ops.perft_part(depth, p, nparts, device=DEV) for p in range(nparts)]     # all enqueued, no sync
+            tot = torch.stack(shares).sum(0).cpu().tolist()
+            assert tot == [want, 0], (depth, nparts, tot)
+    assert ops.perft_distributed(9, device=DEV) == 3005288                 # single process: world of one
+    # an endgame root: game-over leaves inside the breadth-first levels are counted once (by part 0)
+    r = oracle.playout(5, 0, 4)
+    g = 0
+    t = int(r['nplies'][g]) - 6
+    b, w = int(r['black'][t, g]), int(r['white'][t, g])
+    turn = 1 if t % 2 == 0 else 2
+    for d in (5, 8, 12):
+        want = oracle.perft(d, b, w, turn)
+        assert ops.perft(d, b, w, turn, device=DEV) == want
+        assert sum(int(ops.perft_part(d, p, 4, b, w, turn, device=DEV)[0]) for p in range(4)) == want
+    # too little scratch is reported, not overrun
+    ws = torch.empty(256 + 16 + 4 * 64 * 8, dtype=torch.uint8, device=DEV)
+    import ctypes
+    res = ctypes.c_uint64()
+    rc = L.othello_perft(ops.START_BLACK, ops.START_WHITE, 1, 9, ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                         ctypes.byref(res), None)
+    assert rc == -2
