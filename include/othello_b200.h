@@ -202,12 +202,42 @@ int othello_value_records(const uint64_t *traj_black, const uint64_t *traj_white
                           int32_t t_max, const double *decay /* [t_max+1] */, const int64_t *rec_base,
                           uint64_t *keys, double *targets, void *stream);
 
-/* __update_state_map (:50-62) for runs of records that share a key: segment s covers
- * targets[seg_start[s] .. seg_start[s+1]) in update order and starts from init[s] (0 = key not in the
- * table); V = new if V == 0 else V*(1-a) + new*a, evaluated sequentially in fp64 with the reference's
- * rounding (no fused multiply-add).  out[s] = the value the table holds afterwards. */
-int othello_value_smooth(const double *targets, const int64_t *seg_start, const double *init, double a, double *out,
-                         int64_t n_seg, void *stream);
+/* Stable sort of n (key, value) records by the low `key_bits` bits of the key -- hand-written LSD radix
+ * sort, 8 bits per pass, records of equal keys keep their order (= the reference's update order).  The
+ * result is left in keys / values; *_alt are scratch of the same size.  workspace: DEVICE,
+ * >= othello_sort_workspace_bytes(n).  n < 2^32. */
+int64_t othello_sort_workspace_bytes(int64_t n);
+int othello_sort_records(uint64_t *keys, double *values, uint64_t *keys_alt, double *values_alt, int64_t n,
+                         int32_t key_bits, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Stable partition of the records by the rank that owns their key when the table is sharded over `world`
+ * GPUs (one all_to_all of records per batch): out = records of owner 0, then owner 1, ...,
+ * order preserved inside an owner; owner_counts[world] (DEVICE int64) receives the block sizes. */
+int othello_partition_records(const uint64_t *keys, const double *values, uint64_t *keys_out, double *values_out,
+                              int64_t n, int32_t world, int64_t *owner_counts, void *workspace, int64_t workspace_bytes,
+                              void *stream);
+
+/* The table: open-addressing hash (slot_keys[2^log2_capacity] uint64, 0 = empty; slot_idx int32) from key
+ * to an index into the dense arrays dense_keys / dense_values.  __update_state_map (:50-62) for a SORTED
+ * batch of records in two steps, so that the caller can grow the arrays in between:
+ *   othello_table_probe: marks the heads of the runs of equal keys and looks them up; counters[1] (DEVICE
+ *     int64[2]) = number of keys the batch adds.  workspace: DEVICE, >= othello_table_workspace_bytes(n),
+ *     handed unchanged to othello_table_apply.
+ *   othello_table_apply: every run is walked in order by one thread, V = new if V == 0 else V*(1-a) + new*a
+ *     in fp64 with the reference's rounding (no fused multiply-add), from the stored value (0 for a new
+ *     key: `set(key, 0)`, :52-53).  New keys are appended to the dense arrays at n_before.. in key order and
+ *     entered into the hash; needs 2 * (n_before + new) <= 2^log2_capacity. */
+int64_t othello_table_workspace_bytes(int64_t n);
+int othello_table_probe(const uint64_t *sorted_keys, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
+                        int32_t log2_capacity, void *workspace, int64_t workspace_bytes, int64_t *counters, void *stream);
+int othello_table_apply(const uint64_t *sorted_keys, const double *sorted_targets, int64_t n, double a,
+                        uint64_t *slot_keys, int32_t *slot_idx, int32_t log2_capacity, uint64_t *dense_keys,
+                        double *dense_values, int64_t n_before, const void *workspace, void *stream);
+/* (re)build the hash from dense_keys[0..n) (slot arrays zeroed by the caller); key -> dense index or -1 */
+int othello_table_rehash(const uint64_t *dense_keys, int64_t n, uint64_t *slot_keys, int32_t *slot_idx,
+                         int32_t log2_capacity, void *stream);
+int othello_table_lookup(const uint64_t *query, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
+                         int32_t log2_capacity, int32_t *index, void *stream);
 
 /* packed key -> the 10 integers of counts() (features[n][10]) */
 int othello_unpack_keys(const uint64_t *keys, int32_t *features, int64_t n, void *stream);

@@ -321,6 +321,74 @@ def make_paramgen():
     return cases
 
 
+def reference_update_rule(ns):
+    """The reference's own value-table update, EXECUTED from its source text: the two methods
+    ``__update_state_for_a_book`` / ``__update_state_map`` (progress_position_moves_learn.py:37-62) and the
+    constants of ``__init__`` (:19-25) are cut out of /root/reference/progress_position_moves_learn.py and
+    compiled as they stand (the module itself cannot be imported: py2 print statements, redis / pyres /
+    sklearn-era imports).  Substitutions: the py2 debug statement ``print book[0]`` is dropped; nothing else.
+    ``self._param_store()`` -- Redis in the reference -- is a dict with the three calls the text makes
+    (exists / set / get); Redis hands strings back, so ``get`` returns ``repr`` text like redis-py would.
+    Returns an object whose ``update(book_id, book)`` is the reference's ``__update_state_for_a_book``."""
+    import re
+    import textwrap
+    from . import build_ref
+    path = os.path.join(build_ref.REF_SRC, "progress_position_moves_learn.py")
+    text = open(path).read()
+    lines = text.split("\n")
+    start = next(i for i, ln in enumerate(lines) if re.match(r"\s+def __update_state_for_a_book\(", ln))
+    end = next(i for i, ln in enumerate(lines) if i > start and ln.strip() == "# Learning related functions")
+    body = [ln for ln in lines[start:end] if ln.strip() != "print book[0]       # terminal book"]
+    assert len(body) == end - start - 1, "the py2 debug print was expected exactly once"
+    consts = dict(re.findall(r"self\.(a|l) = ([0-9.]+)", text))
+    src = "class ReferenceRule(object):\n" + "\n".join(body) + "\n"
+    src += textwrap.dedent("""
+        def update(self, book_id, book):
+            return self._ReferenceRule__update_state_for_a_book(book_id, book)
+    """).replace("\n", "\n    ")
+
+    class Store(object):
+        def __init__(self):
+            self.d = {}
+
+        def exists(self, key):
+            return tuple(key) in self.d
+
+        def set(self, key, value):
+            self.d[tuple(key)] = repr(value)         # what lands in Redis (py2.7 / py3 repr round-trips floats)
+
+        def get(self, key):
+            return self.d[tuple(key)]
+
+    scope = {"board_from_a_book": ns.parameter.board_from_a_book}
+    exec(compile(src, path + ":37-62", "exec"), scope)
+    rule = scope["ReferenceRule"]()
+    rule.a, rule.l = float(consts["a"]), float(consts["l"])
+    rule.parameter = ns.ppml.ProgressPositionMovesParameter()
+    store = Store()
+    rule._param_store = lambda: store
+    rule.store = store
+    return rule
+
+
+def make_value_table(ns, games, batches=((0, 12), (12, 24))):
+    """the value table the reference builds from the first 24 golden games (seed 0, uniform random, game ids
+    0..23), in two batches: books sorted by turn and reversed, terminal record first (replearn.py:37-38)"""
+    rule = reference_update_rule(ns)
+    out = {"a": rule.a, "l": rule.l, "seed": 0, "batches": [list(b) for b in batches], "after": []}
+    for lo, hi in batches:
+        for gid in range(lo, hi):
+            g = games[gid]
+            assert g['seed'] == 0 and g['gid'] == gid and g['policy'] == 0
+            recs = [{'book': p['ser'][:64], 'whosturn': p['ser'][65], 'turn': str(p['nturn']), 'end': p['over']}
+                    for p in g['positions']]
+            book = list(reversed(sorted(recs, key=lambda x: int(x['turn']))))
+            assert book[0]['end']
+            rule.update(gid, book)
+        out["after"].append({k[2]: float(v).hex() for k, v in rule.store.d.items()})
+    return out
+
+
 def dump(name, obj):
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name)
@@ -354,6 +422,7 @@ def main():
     dump("games.json.gz", games)
     dump("probe.json.gz", make_probe(ns, games))
     dump("paramgen.json.gz", make_paramgen())
+    dump("value_table.json.gz", make_value_table(ns, games))
     n_pass = sum(1 for g in games for p in g['plies'] if p['move'] == 64)
     print("games=%d plies=%d passes=%d" % (len(games), sum(len(g['plies']) for g in games), n_pass))
     return 0

@@ -68,7 +68,14 @@ SIGNATURES = {
     "othello_learn_stats": (ctypes.c_int, [vp, vp, vp]),
     "othello_learn_solve": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "othello_value_records": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
-    "othello_value_smooth": (ctypes.c_int, [vp, vp, vp, ctypes.c_double, vp, i64, vp]),
+    "othello_sort_workspace_bytes": (i64, [i64]),
+    "othello_sort_records": (ctypes.c_int, [vp, vp, vp, vp, i64, i32, vp, i64, vp]),
+    "othello_partition_records": (ctypes.c_int, [vp, vp, vp, vp, i64, i32, vp, vp, i64, vp]),
+    "othello_table_workspace_bytes": (i64, [i64]),
+    "othello_table_probe": (ctypes.c_int, [vp, i64, vp, vp, i32, vp, i64, vp, vp]),
+    "othello_table_apply": (ctypes.c_int, [vp, vp, i64, ctypes.c_double, vp, vp, i32, vp, vp, i64, vp, vp]),
+    "othello_table_rehash": (ctypes.c_int, [vp, i64, vp, vp, i32, vp]),
+    "othello_table_lookup": (ctypes.c_int, [vp, i64, vp, vp, i32, vp, vp]),
     "othello_unpack_keys": (ctypes.c_int, [vp, vp, i64, vp]),
     "othello_int32_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "othello_int32_dual_peak_kernel": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),

@@ -9,10 +9,11 @@
 //     V   = V * (1 - a) + new * a   otherwise                a = 0.03
 // Different keys are independent; the updates of ONE key form a sequential fp64 recurrence whose
 // result depends on the order.  So: (1) records_kernel emits (key, new) for every (position, side)
-// at its position in the reference's order; (2) the host side groups equal keys with a STABLE sort
-// (order inside a key is preserved); (3) smooth_kernel walks each key's run sequentially, one thread
-// per key, with the reference's exact operation order (two roundings for the products, one for the
-// sum -- no FMA contraction), starting from the value already in the table.
+// at its position in the reference's order; (2) a hand-written STABLE radix sort groups equal keys and
+// keeps the order inside a key; (3) every run of equal keys is walked sequentially by one thread with the
+// reference's exact operation order (two roundings for the products, one for the sum -- no FMA
+// contraction), starting from the value already in the table, which is an open-addressing hash table in
+// HBM (key -> dense index) next to dense key / value arrays: no merge, no re-sort of the table per batch.
 #include "common.cuh"
 #include "fastboard.cuh"
 
@@ -69,29 +70,297 @@ __device__ __forceinline__ double smooth_step(double v, double nv, double keep, 
     return (v == 0.0) ? nv : __dadd_rn(__dmul_rn(v, keep), __dmul_rn(nv, a));      // :56-61
 }
 
-// One thread per key walks its run in update order.  The recurrence is sequential by definition; the
-// loads are not, so they are issued eight at a time ahead of the dependent fp64 chain (the opening
-// positions are visited by every game: their runs are 2 x n_games long).
-__global__ void __launch_bounds__(kThreads) smooth_kernel(const double *__restrict__ targets,
-                                                          const int64_t *__restrict__ seg_start,
-                                                          const double *__restrict__ init, double a,
-                                                          double *__restrict__ out, int64_t n_seg)
+// ---- stable LSD radix sort of (key, value) records ------------------------------------------------
+// Grouping the records of one key while keeping their update order is a STABLE sort by key.  43-bit
+// keys = 6 passes of 8 bits; every pass is histogram -> per-digit row scan -> stable scatter.  A tile is
+// 4096 consecutive records; inside a tile warp w owns records [512 w, 512 (w + 1)) in 16 coalesced rows,
+// ranks them per digit with match.any (lanes holding the same digit find each other, the lowest lane
+// advances the warp's running counter), and the 8 warps are ordered through a per-digit prefix.
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortRows = 16;
+constexpr int kTile = kSortThreads * kSortRows;
+constexpr unsigned kAll = 0xffffffffu;
+
+__device__ __forceinline__ unsigned owner_of(u64 key, unsigned world)
 {
-    const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (s >= n_seg) return;
-    const double keep = __dsub_rn(1.0, a);                                          // (1 - self.a)
-    double v = init[s];
-    int64_t i = seg_start[s];
-    const int64_t e = seg_start[s + 1];
-    for (; i + 8 <= e; i += 8) {
-        double x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = __ldg(targets + i + j);
-#pragma unroll
-        for (int j = 0; j < 8; j++) v = smooth_step(v, x[j], keep, a);
+    const u64 h = key * 0x9E3779B97F4A7C15ull;
+    return (unsigned)(((h >> 32) * (u64)world) >> 32);
+}
+// MODE 0: 8 bits of the key at `shift`; MODE 1: the rank that owns the key in a table sharded over `world` GPUs
+template <int MODE> __device__ __forceinline__ unsigned digit_of(u64 key, int shift, unsigned world)
+{
+    return MODE == 0 ? (unsigned)(key >> shift) & 255u : owner_of(key, world);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const u64 *__restrict__ keys, int64_t n, int shift,
+                                                                 unsigned world, unsigned *__restrict__ counts, int64_t tiles)
+{
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+#pragma unroll 4
+    for (int r = 0; r < kSortRows; r++) {
+        const int64_t i = base + r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[digit_of<MODE>(keys[i], shift, world)], 1u);
     }
-    for (; i < e; i++) v = smooth_step(v, targets[i], keep, a);
-    out[s] = v;
+    __syncthreads();
+    counts[(int64_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];          // digit-major
+}
+
+// exclusive scan of 256 values held one per thread (CTA of 256 threads); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ unsigned block_scan_256(unsigned v, unsigned *s_warp, unsigned *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kAll, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) {
+        const unsigned c = s_warp[w];
+        if (w < warp) before += c;
+        sum += c;
+    }
+    __syncthreads();
+    if (total) *total = sum;
+    return before + incl - v;
+}
+
+// one CTA per digit: exclusive scan of its row of per-tile counts (in place), row total -> totals[digit]
+__global__ void __launch_bounds__(kSortThreads) sort_rowscan_kernel(unsigned *__restrict__ counts, int64_t tiles,
+                                                                    unsigned *__restrict__ totals)
+{
+    __shared__ unsigned s_warp[kSortWarps];
+    unsigned *row = counts + (int64_t)blockIdx.x * tiles;
+    unsigned carry = 0;
+    for (int64_t base = 0; base < tiles; base += kSortThreads * 8) {
+        unsigned v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t i = base + (int64_t)threadIdx.x * 8 + j;
+            v[j] = i < tiles ? row[i] : 0u;
+            sum += v[j];
+        }
+        unsigned total;
+        unsigned at = carry + block_scan_256(sum, s_warp, &total);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t i = base + (int64_t)threadIdx.x * 8 + j;
+            if (i < tiles) row[i] = at;
+            at += v[j];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const u64 *__restrict__ keys_in,
+                                                                    const double *__restrict__ vals_in,
+                                                                    u64 *__restrict__ keys_out, double *__restrict__ vals_out,
+                                                                    int64_t n, int shift, unsigned world,
+                                                                    const unsigned *__restrict__ counts,
+                                                                    const unsigned *__restrict__ totals, int64_t tiles)
+{
+    __shared__ unsigned s_warp[kSortWarps];
+    __shared__ unsigned whist[kSortWarps][256];       // per warp and digit: count, then running output position
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // where this tile's records of digit d start: all smaller digits + this digit's records of earlier tiles
+    const unsigned dbase = block_scan_256(totals[threadIdx.x], s_warp, nullptr) +
+                           counts[(int64_t)threadIdx.x * tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) whist[w][threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kTile + warp * (kSortRows * 32) + lane;
+    u64 key[kSortRows];
+#pragma unroll
+    for (int r = 0; r < kSortRows; r++) {
+        const int64_t i = base + r * 32;
+        key[r] = i < n ? keys_in[i] : 0ull;
+        if (i < n) atomicAdd(&whist[warp][digit_of<MODE>(key[r], shift, world)], 1u);
+    }
+    __syncthreads();
+    {
+        unsigned at = dbase;                          // thread d orders the warps' runs of digit d
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            const unsigned c = whist[w][threadIdx.x];
+            whist[w][threadIdx.x] = at;
+            at += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRows; r++) {
+        const int64_t i = base + r * 32;
+        const bool valid = i < n;
+        const unsigned vmask = __ballot_sync(kAll, valid);
+        if (valid) {
+            const unsigned d = digit_of<MODE>(key[r], shift, world);
+            const unsigned peers = __match_any_sync(vmask, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned at = 0;
+            if (lane == leader) { at = whist[warp][d]; whist[warp][d] = at + __popc(peers); }
+            at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
+            keys_out[at] = key[r];
+            vals_out[at] = vals_in[i];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void export_totals_kernel(const unsigned *__restrict__ totals, int64_t *__restrict__ out, int count)
+{
+    if (threadIdx.x < count) out[threadIdx.x] = (int64_t)totals[threadIdx.x];
+}
+
+// ---- the table: open addressing key -> dense index, dense key / value arrays --------------------------
+// slot_keys[h] = key (0 = empty: a key's top bits are its disc count >= 4), slot_idx[h] = index into the
+// dense arrays.  Linear probing from the high bits of a multiplicative hash; capacity is a power of two.
+__device__ __forceinline__ u64 slot_of(u64 key, int log2cap) { return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2cap); }
+
+__device__ __forceinline__ int table_find(u64 key, const u64 *slot_keys, const int32_t *slot_idx, int log2cap)
+{
+    const u64 mask = (1ull << log2cap) - 1ull;
+    for (u64 h = slot_of(key, log2cap);; h = (h + 1) & mask) {
+        const u64 cur = slot_keys[h];
+        if (cur == key) return slot_idx[h];
+        if (cur == 0ull) return -1;
+    }
+}
+
+// pass 1 over the sorted records: which records start a run (a "head"), which heads are new keys;
+// tag[i] = dense index of the key (head, known), -1 (head, new), -2 (not a head); new heads per tile -> tile_new
+__global__ void __launch_bounds__(kSortThreads) table_probe_kernel(const u64 *__restrict__ keys, int64_t n,
+                                                                   const u64 *__restrict__ slot_keys,
+                                                                   const int32_t *__restrict__ slot_idx, int log2cap,
+                                                                   int32_t *__restrict__ tag, unsigned *__restrict__ tile_new)
+{
+    __shared__ unsigned s_new;
+    if (threadIdx.x == 0) s_new = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    unsigned mine = 0;
+    for (int r = 0; r < kSortRows; r++) {
+        const int64_t i = base + r * kSortThreads + threadIdx.x;
+        if (i >= n) break;
+        const u64 k = keys[i];
+        int t = -2;
+        if (i == 0 || keys[i - 1] != k) {
+            t = table_find(k, slot_keys, slot_idx, log2cap);
+            if (t < 0) mine++;
+        }
+        tag[i] = t;
+    }
+    if (mine) atomicAdd(&s_new, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_new[blockIdx.x] = s_new;
+}
+
+// exclusive scan of tile_new (one CTA), total -> counters[1]; counters[0] = keys in the table before the batch
+__global__ void __launch_bounds__(kSortThreads) table_scan_kernel(unsigned *__restrict__ tile_new, int64_t tiles,
+                                                                  int64_t *__restrict__ counters)
+{
+    __shared__ unsigned s_warp[kSortWarps];
+    unsigned carry = 0;
+    for (int64_t base = 0; base < tiles; base += kSortThreads) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned v = i < tiles ? tile_new[i] : 0u;
+        unsigned total;
+        const unsigned at = carry + block_scan_256(v, s_warp, &total);
+        if (i < tiles) tile_new[i] = at;
+        carry += total;
+    }
+    if (threadIdx.x == 0) counters[1] = (int64_t)carry;
+}
+
+// pass 2: every head walks its run in update order (:56-61, sequential by definition; loads are issued
+// eight at a time ahead of the dependent fp64 chain).  New keys get dense indices in sorted-key order --
+// n_before + new heads in earlier tiles + new heads earlier in this tile -- so the table's layout does not
+// depend on the scheduling of the launch.
+__global__ void __launch_bounds__(kSortThreads) table_apply_kernel(const u64 *__restrict__ keys,
+                                                                   const double *__restrict__ targets, int64_t n, double a,
+                                                                   const int32_t *__restrict__ tag,
+                                                                   const unsigned *__restrict__ tile_base,
+                                                                   u64 *__restrict__ slot_keys, int32_t *__restrict__ slot_idx,
+                                                                   int log2cap, u64 *__restrict__ dense_keys,
+                                                                   double *__restrict__ dense_values, int64_t n_before)
+{
+    __shared__ unsigned s_warp[kSortWarps];
+    const double keep = __dsub_rn(1.0, a);                                          // (1 - self.a)
+    const u64 mask = (1ull << log2cap) - 1ull;
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    unsigned before = tile_base[blockIdx.x];
+    // thread t owns records [base + 16 t, base + 16 t + 16): consecutive, so a per-thread count + block scan ranks the new heads
+    int32_t tg[kSortRows];
+    unsigned mine = 0;
+    const int64_t first = base + (int64_t)threadIdx.x * kSortRows;
+#pragma unroll
+    for (int r = 0; r < kSortRows; r++) {
+        tg[r] = first + r < n ? tag[first + r] : -2;
+        mine += tg[r] == -1;
+    }
+    unsigned rank = before + block_scan_256(mine, s_warp, nullptr);
+#pragma unroll 1
+    for (int r = 0; r < kSortRows; r++) {
+        if (tg[r] == -2) continue;
+        const int64_t i = first + r;
+        const u64 k = keys[i];
+        int64_t di;
+        double v;
+        if (tg[r] >= 0) {
+            di = tg[r];
+            v = dense_values[di];
+        } else {
+            di = n_before + (int64_t)rank++;
+            v = 0.0;                                                                // `if not exists: set(key, 0)` (:52-53)
+            dense_keys[di] = k;
+            for (u64 h = slot_of(k, log2cap);; h = (h + 1) & mask)                  // keys of one batch are distinct: plain CAS claim
+                if (atomicCAS((unsigned long long *)&slot_keys[h], 0ull, (unsigned long long)k) == 0ull) { slot_idx[h] = (int32_t)di; break; }
+        }
+        for (int64_t j = i;; j += 8) {                                              // the run starts at its head
+            double x[8];
+            bool same[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                same[q] = j + q < n && keys[j + q] == k;
+                x[q] = same[q] ? __ldg(targets + j + q) : 0.0;
+            }
+            bool more = true;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (more && same[q]) v = smooth_step(v, x[q], keep, a);
+                else more = false;
+            }
+            if (!more) break;
+        }
+        dense_values[di] = v;
+    }
+}
+
+__global__ void table_rehash_kernel(const u64 *__restrict__ dense_keys, int64_t n, u64 *__restrict__ slot_keys,
+                                    int32_t *__restrict__ slot_idx, int log2cap)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = dense_keys[i], mask = (1ull << log2cap) - 1ull;
+    for (u64 h = slot_of(k, log2cap);; h = (h + 1) & mask)
+        if (atomicCAS((unsigned long long *)&slot_keys[h], 0ull, (unsigned long long)k) == 0ull) { slot_idx[h] = (int32_t)i; break; }
+}
+
+__global__ void table_lookup_kernel(const u64 *__restrict__ query, int64_t n, const u64 *__restrict__ slot_keys,
+                                    const int32_t *__restrict__ slot_idx, int log2cap, int32_t *__restrict__ index)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) index[i] = table_find(query[i], slot_keys, slot_idx, log2cap);
 }
 
 __global__ void __launch_bounds__(kThreads) unpack_kernel(const u64 *__restrict__ keys, int32_t *__restrict__ out, int64_t n)
@@ -105,6 +374,18 @@ __global__ void __launch_bounds__(kThreads) unpack_kernel(const u64 *__restrict_
         out[10 * i + f] = (int32_t)(k & ((1ull << widths[f]) - 1));
         k >>= widths[f];
     }
+}
+
+// one pass: histogram -> row scan -> stable scatter (in -> out)
+template <int MODE>
+int sort_pass(const u64 *kin, const double *vin, u64 *kout, double *vout, int64_t n, int shift, unsigned world,
+                     unsigned *counts, unsigned *totals, cudaStream_t s)
+{
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    sort_hist_kernel<MODE><<<(unsigned)tiles, kSortThreads, 0, s>>>(kin, n, shift, world, counts, tiles);
+    sort_rowscan_kernel<<<256, kSortThreads, 0, s>>>(counts, tiles, totals);
+    sort_scatter_kernel<MODE><<<(unsigned)tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, world, counts, totals, tiles);
+    return ob_launch_status();
 }
 
 }  // namespace
@@ -127,13 +408,112 @@ int othello_value_records(const uint64_t *traj_black, const uint64_t *traj_white
     return ob_launch_status();
 }
 
-int othello_value_smooth(const double *targets, const int64_t *seg_start, const double *init, double a, double *out,
-                         int64_t n_seg, void *stream)
+int64_t othello_sort_workspace_bytes(int64_t n)
 {
-    OB_CHECK_ARGS(n_seg >= 0);
-    if (n_seg == 0) return 0;
-    OB_CHECK_ARGS(targets && seg_start && init && out);
-    smooth_kernel<<<ob_blocks(n_seg, kThreads), kThreads, 0, (cudaStream_t)stream>>>(targets, seg_start, init, a, out, n_seg);
+    const int64_t tiles = n > 0 ? (n + kTile - 1) / kTile : 1;
+    return (256 * tiles + 256) * (int64_t)sizeof(unsigned);
+}
+
+int othello_sort_records(uint64_t *keys, double *values, uint64_t *keys_alt, double *values_alt, int64_t n,
+                         int32_t key_bits, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && key_bits >= 1 && key_bits <= 64);
+    if (n <= 1) return 0;
+    OB_CHECK_ARGS(keys && values && keys_alt && values_alt && workspace && n < (1ll << 32));
+    if (workspace_bytes < othello_sort_workspace_bytes(n)) return OTHELLO_E_WORKSPACE;
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    unsigned *counts = (unsigned *)workspace, *totals = counts + 256 * tiles;
+    int passes = (key_bits + 7) / 8;
+    passes += passes & 1;                                   // an even number of passes ends in the caller's buffers
+    u64 *k[2] = {(u64 *)keys, (u64 *)keys_alt};
+    double *v[2] = {values, values_alt};
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        int rc = shift < 64 ? sort_pass<0>(k[p & 1], v[p & 1], k[(p + 1) & 1], v[(p + 1) & 1], n, shift, 0u, counts, totals,
+                                           (cudaStream_t)stream)
+                            : OTHELLO_E_INVALID;
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int othello_partition_records(const uint64_t *keys, const double *values, uint64_t *keys_out, double *values_out,
+                              int64_t n, int32_t world, int64_t *owner_counts, void *workspace, int64_t workspace_bytes,
+                              void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && world >= 1 && world <= 256 && owner_counts);
+    OB_CHECK_ARGS(workspace && workspace_bytes >= othello_sort_workspace_bytes(n));
+    const int64_t tiles = n > 0 ? (n + kTile - 1) / kTile : 1;
+    unsigned *counts = (unsigned *)workspace, *totals = counts + 256 * tiles;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        OB_CUDA(cudaMemsetAsync(owner_counts, 0, sizeof(int64_t) * world, s));
+        return 0;
+    }
+    OB_CHECK_ARGS(keys && values && keys_out && values_out && n < (1ll << 32));
+    int rc = sort_pass<1>((const u64 *)keys, values, (u64 *)keys_out, values_out, n, 0, (unsigned)world, counts, totals, s);
+    if (rc) return rc;
+    export_totals_kernel<<<1, 256, 0, s>>>(totals, owner_counts, world);
+    return ob_launch_status();
+}
+
+int64_t othello_table_workspace_bytes(int64_t n)
+{
+    const int64_t tiles = n > 0 ? (n + kTile - 1) / kTile : 1;
+    return n * (int64_t)sizeof(int32_t) + tiles * (int64_t)sizeof(unsigned) + 256;
+}
+
+int othello_table_probe(const uint64_t *sorted_keys, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
+                        int32_t log2_capacity, void *workspace, int64_t workspace_bytes, int64_t *counters, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && counters && log2_capacity >= 4 && log2_capacity <= 31);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) { OB_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(int64_t), s)); return 0; }
+    OB_CHECK_ARGS(sorted_keys && slot_keys && slot_idx && workspace && workspace_bytes >= othello_table_workspace_bytes(n));
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    int32_t *tag = (int32_t *)workspace;
+    unsigned *tile_new = (unsigned *)((char *)workspace + ((n * sizeof(int32_t) + 255) & ~(size_t)255));
+    table_probe_kernel<<<(unsigned)tiles, kSortThreads, 0, s>>>((const u64 *)sorted_keys, n, (const u64 *)slot_keys, slot_idx,
+                                                               log2_capacity, tag, tile_new);
+    table_scan_kernel<<<1, kSortThreads, 0, s>>>(tile_new, tiles, counters);
+    return ob_launch_status();
+}
+
+int othello_table_apply(const uint64_t *sorted_keys, const double *sorted_targets, int64_t n, double a,
+                        uint64_t *slot_keys, int32_t *slot_idx, int32_t log2_capacity, uint64_t *dense_keys,
+                        double *dense_values, int64_t n_before, const void *workspace, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && n_before >= 0 && log2_capacity >= 4 && log2_capacity <= 31);
+    if (n == 0) return 0;
+    OB_CHECK_ARGS(sorted_keys && sorted_targets && slot_keys && slot_idx && dense_keys && dense_values && workspace);
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    const int32_t *tag = (const int32_t *)workspace;
+    const unsigned *tile_base = (const unsigned *)((const char *)workspace + ((n * sizeof(int32_t) + 255) & ~(size_t)255));
+    table_apply_kernel<<<(unsigned)tiles, kSortThreads, 0, (cudaStream_t)stream>>>(
+        (const u64 *)sorted_keys, sorted_targets, n, a, tag, tile_base, (u64 *)slot_keys, slot_idx, log2_capacity,
+        (u64 *)dense_keys, dense_values, n_before);
+    return ob_launch_status();
+}
+
+int othello_table_rehash(const uint64_t *dense_keys, int64_t n, uint64_t *slot_keys, int32_t *slot_idx,
+                         int32_t log2_capacity, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && log2_capacity >= 4 && log2_capacity <= 31 && n <= (1ll << log2_capacity) / 2);
+    if (n == 0) return 0;
+    OB_CHECK_ARGS(dense_keys && slot_keys && slot_idx);
+    table_rehash_kernel<<<ob_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64 *)dense_keys, n, (u64 *)slot_keys,
+                                                                              slot_idx, log2_capacity);
+    return ob_launch_status();
+}
+
+int othello_table_lookup(const uint64_t *query, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
+                         int32_t log2_capacity, int32_t *index, void *stream)
+{
+    OB_CHECK_ARGS(n >= 0 && log2_capacity >= 4 && log2_capacity <= 31);
+    if (n == 0) return 0;
+    OB_CHECK_ARGS(query && slot_keys && slot_idx && index);
+    table_lookup_kernel<<<ob_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64 *)query, n, (const u64 *)slot_keys,
+                                                                             slot_idx, log2_capacity, index);
     return ob_launch_status();
 }
 

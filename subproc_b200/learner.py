@@ -290,8 +290,7 @@ class ProgressPositionMovesLearn(object):
         self.table = None
         if state['table_keys'] is not None:
             self.table = value_table.ValueTable(device=device, a=self.a, lam=self.l)
-            self.table.keys = state['table_keys'].to(self.table.device)
-            self.table.values = state['table_values'].to(self.table.device)
+            self.table.load_state(state['table_keys'], state['table_values'])
         return self
 
     # ---- the reference's book-driven entry point ---------------------------------------------

@@ -3,8 +3,9 @@
 ``ValueTable.update_from_playout`` does what ``learn_and_update_batch`` does book by book through
 Redis (progress_position_moves_learn.py:37-62,88-91): every (position, side) of every game updates the
 float stored under its ``counts()`` 10-tuple, in the reference's order.  The result is bit-identical to
-running the reference's loop (tests/test_gpu_value_table.py checks it against a dict-based
-restatement); the table lives in HBM as a sorted key array + value array instead of Redis strings.
+running the reference's loop (tests/test_gpu_value_table.py checks it against vectors produced by
+executing the reference's own update methods, tests/golden/value_table.json.gz); the table lives in HBM
+as a hash from key to a dense (key, value) array instead of Redis strings.
 
 ``fit_parameter`` is the reference's per-shard fit on a sample of the TABLE (:66-86,160-184): draw
 keys at random, keep those whose disc count is in the shard, de-duplicate, bootstrap-resample, OLS with
@@ -21,6 +22,7 @@ import torch
 from . import _lib, ops, learner
 
 WIDTHS = (7, 6, 3, 4, 3, 4, 4, 5, 3, 4)          # discs mobility a b c d e f g h -> 43 bits
+KEY_BITS = sum(WIDTHS)
 
 
 def pack_key(features):
@@ -39,18 +41,74 @@ def unpack_key(k):
 
 
 class ValueTable(object):
+    """The table in HBM: dense ``keys`` / ``values`` arrays (in order of first appearance: batch by batch,
+    ascending key inside a batch) plus an open-addressing hash key -> dense index.  Everything on the update
+    path is a hand-written kernel of csrc/value_table.cu: records, stable radix sort, probe, apply."""
+
+    MIN_LOG2_CAPACITY = 12
+
     def __init__(self, device=None, a=0.03, lam=0.90):
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
         self.a = a
         self.lam = lam
-        self.keys = torch.empty(0, dtype=torch.int64, device=self.device)      # sorted, unique
-        self.values = torch.empty(0, dtype=torch.float64, device=self.device)
+        self.n = 0                                             # keys in the table
+        self._keys = torch.empty(0, dtype=torch.int64, device=self.device)
+        self._values = torch.empty(0, dtype=torch.float64, device=self.device)
+        self._log2cap = self.MIN_LOG2_CAPACITY
+        self._slot_keys = torch.zeros(1 << self._log2cap, dtype=torch.int64, device=self.device)
+        self._slot_idx = torch.zeros(1 << self._log2cap, dtype=torch.int32, device=self.device)
+        self._counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._ws = {}
 
     def __len__(self):
-        return int(self.keys.numel())
+        return self.n
+
+    @property
+    def keys(self):
+        return self._keys[:self.n]
+
+    @property
+    def values(self):
+        return self._values[:self.n]
+
+    def load_state(self, keys, values):
+        """adopt dense key / value arrays (a checkpoint) and rebuild the hash"""
+        self.n = int(keys.numel())
+        self._keys = keys.to(self.device, torch.int64).contiguous().clone()
+        self._values = values.to(self.device, torch.float64).contiguous().clone()
+        self._log2cap = self.MIN_LOG2_CAPACITY
+        self._reserve(self.n, force=True)
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _scratch(self, name, nbytes):
+        """grow-only device scratch, reused by every update"""
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = self._ws[name] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return t
+
+    def _reserve(self, n_total, force=False):
+        """room for n_total keys: dense arrays grow geometrically, the hash keeps a load factor <= 1/2"""
+        if self._keys.numel() < n_total:
+            cap = max(n_total, 2 * self._keys.numel(), 1024)
+            for name in ("_keys", "_values"):
+                old = getattr(self, name)
+                new = torch.empty(cap, dtype=old.dtype, device=self.device)
+                new[:self.n] = old[:self.n]
+                setattr(self, name, new)
+        log2 = self._log2cap
+        while (1 << log2) < 2 * max(n_total, 1):
+            log2 += 1
+        if log2 != self._log2cap or force:
+            self._log2cap = log2
+            self._slot_keys = torch.zeros(1 << log2, dtype=torch.int64, device=self.device)
+            self._slot_idx = torch.zeros(1 << log2, dtype=torch.int32, device=self.device)
+            P = lambda t: ctypes.c_void_p(t.data_ptr())
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().othello_table_rehash(P(self._keys), self.n, P(self._slot_keys), P(self._slot_idx),
+                                                           log2, self._stream()), "othello_table_rehash")
 
     # ---- update ------------------------------------------------------------------------------
     def records_from_playout(self, po):
@@ -62,7 +120,7 @@ class ValueTable(object):
         total = int(counts.sum().item())
         keys = torch.empty(total, dtype=torch.int64, device=self.device)
         targets = torch.empty(total, dtype=torch.float64, device=self.device)
-        decay = torch.from_numpy(ops.decay_table(po.t_max, self.lam)).to(self.device)
+        decay = ops.decay_tensor(po.t_max, self.lam, self.device)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().othello_value_records(
@@ -70,53 +128,92 @@ class ValueTable(object):
                 P(decay), P(base), P(keys), P(targets), self._stream()), "othello_value_records")
         return keys, targets
 
+    def sort_records(self, keys, targets):
+        """stable sort by key IN PLACE (othello_sort_records): groups a key's records, keeps their order"""
+        n = keys.numel()
+        if n > 1:
+            L = _lib.lib()
+            kalt, valt = torch.empty_like(keys), torch.empty_like(targets)
+            nbytes = int(L.othello_sort_workspace_bytes(n))
+            ws = self._scratch("sort", nbytes)
+            P = lambda t: ctypes.c_void_p(t.data_ptr())
+            with torch.cuda.device(self.device):
+                _lib.check(L.othello_sort_records(P(keys), P(targets), P(kalt), P(valt), n, KEY_BITS, P(ws), nbytes,
+                                                  self._stream()), "othello_sort_records")
+        return keys, targets
+
     def update(self, keys, targets):
-        """apply records (already in update order) to the table"""
-        if keys.numel() == 0:
+        """apply records (in update order) to the table; ``keys`` / ``targets`` are sorted in place"""
+        n = keys.numel()
+        if n == 0:
             return
-        skeys, perm = torch.sort(keys, stable=True)                    # groups keys, keeps the order inside a key
-        stargets = targets[perm]
-        uniq, cnt = torch.unique_consecutive(skeys, return_counts=True)
-        seg = torch.zeros(uniq.numel() + 1, dtype=torch.int64, device=self.device)
-        seg[1:] = torch.cumsum(cnt, 0)
-        init = torch.zeros(uniq.numel(), dtype=torch.float64, device=self.device)
-        if self.keys.numel():
-            pos = torch.searchsorted(self.keys, uniq).clamp_(max=self.keys.numel() - 1)
-            hit = self.keys[pos] == uniq
-            init[hit] = self.values[pos[hit]]
-        out = torch.empty_like(init)
+        L = _lib.lib()
+        self.sort_records(keys, targets)
+        nbytes = int(L.othello_table_workspace_bytes(n))
+        ws = self._scratch("table", nbytes)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().othello_value_smooth(P(stargets), P(seg), P(init), self.a, P(out), uniq.numel(),
-                                                       self._stream()), "othello_value_smooth")
-        if self.keys.numel():
-            keep = torch.ones(self.keys.numel(), dtype=torch.bool, device=self.device)
-            keep[pos[hit]] = False
-            allk = torch.cat([self.keys[keep], uniq])
-            allv = torch.cat([self.values[keep], out])
-            order = torch.argsort(allk)
-            self.keys, self.values = allk[order], allv[order]
-        else:
-            self.keys, self.values = uniq, out
+            _lib.check(L.othello_table_probe(P(keys), n, P(self._slot_keys), P(self._slot_idx), self._log2cap, P(ws), nbytes,
+                                             P(self._counters), self._stream()), "othello_table_probe")
+            n_new = int(self._counters[1].item())                 # the one host round trip of an update: sizing
+            self._reserve(self.n + n_new)
+            _lib.check(L.othello_table_apply(P(keys), P(targets), n, self.a, P(self._slot_keys), P(self._slot_idx),
+                                             self._log2cap, P(self._keys), P(self._values), self.n, P(ws), self._stream()),
+                       "othello_table_apply")
+        self.n += n_new
 
     def update_from_playout(self, po):
         keys, targets = self.records_from_playout(po)
         self.update(keys, targets)
         return keys.numel()
 
+    def update_sharded(self, keys, targets):
+        """One table over all ranks of the default process group: rank r owns the keys with
+        owner_of(key) == r.  Every rank hands in ITS records in its own update order; ranks must hold
+        contiguous, ascending blocks of game ids (rank 0 the lowest), so that records received in rank order
+        are in the global update order.  One all_to_all of (key, target) records per batch; afterwards this
+        rank's table holds its share of the keys with exactly the values of a single-GPU table."""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        L = _lib.lib()
+        n = keys.numel()
+        nbytes = int(L.othello_sort_workspace_bytes(n))
+        ws = self._scratch("sort", nbytes)
+        kout, vout = torch.empty_like(keys), torch.empty_like(targets)
+        counts = torch.zeros(world, dtype=torch.int64, device=self.device)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(L.othello_partition_records(P(keys), P(targets), P(kout), P(vout), n, world, P(counts), P(ws), nbytes,
+                                                   self._stream()), "othello_partition_records")
+        incoming = torch.empty_like(counts)
+        dist.all_to_all_single(incoming, counts)
+        send, recv = counts.cpu().tolist(), incoming.cpu().tolist()
+        rk = torch.empty(sum(recv), dtype=torch.int64, device=self.device)
+        rv = torch.empty(sum(recv), dtype=torch.float64, device=self.device)
+        dist.all_to_all_single(rk, kout, recv, send)
+        dist.all_to_all_single(rv, vout, recv, send)
+        self.update(rk, rv)                                       # blocks arrive in rank order = update order
+        return rk.numel()
+
     # ---- read --------------------------------------------------------------------------------
+    def lookup(self, keys):
+        """dense index of every key (int64 tensor) or -1"""
+        out = torch.empty(keys.numel(), dtype=torch.int32, device=self.device)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().othello_table_lookup(P(keys), keys.numel(), P(self._slot_keys), P(self._slot_idx),
+                                                       self._log2cap, P(out), self._stream()), "othello_table_lookup")
+        return out
+
     def get(self, features):
         """value stored under a counts() 10-tuple, or None"""
-        k = pack_key(features)
         if not len(self):
             return None
-        pos = int(torch.searchsorted(self.keys, torch.tensor([k], dtype=torch.int64, device=self.device)).item())
-        if pos < len(self) and int(self.keys[pos].item()) == k:
-            return float(self.values[pos].item())
-        return None
+        at = int(self.lookup(torch.tensor([pack_key(features)], dtype=torch.int64, device=self.device)).item())
+        return float(self._values[at].item()) if at >= 0 else None
 
     def features(self, keys=None):
-        keys = self.keys if keys is None else keys
+        keys = (self.keys if keys is None else keys).contiguous()
         out = torch.empty((keys.numel(), 10), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().othello_unpack_keys(ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(out.data_ptr()),

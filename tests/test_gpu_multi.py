@@ -57,3 +57,50 @@ def test_two_ranks_equal_one_gpu_on_the_union_of_games():
     L = learner.ProgressPositionMovesLearn()
     L.learn_from_acc(whole)
     assert L.read_parameters() == got[0][4]                        # ... and identical to the single-GPU fit
+
+
+def _table_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from subproc_b200 import ops, value_table
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    vt = value_table.ValueTable(device=dev)
+    per = 3000
+    for batch in range(2):                                        # the sharded table carries over between batches
+        lo = (batch * world + rank) * per                         # contiguous ascending blocks of game ids per rank
+        po = ops.playout(per, seed=23, gid0=lo, device=dev)
+        keys, targets = vt.records_from_playout(po)
+        vt.update_sharded(keys, targets)
+    q.put((rank, vt.keys.cpu().numpy(), vt.values.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < WORLD, reason="needs >= 2 GPUs")
+def test_key_sharded_value_table_equals_the_single_gpu_table():
+    """SURVEY 8(e): the exact value table sharded by key over the ranks, one all_to_all of records per batch;
+    the union of the ranks' shares must be the single-GPU table, bit for bit"""
+    import torch.multiprocessing as mp
+    from subproc_b200 import ops, value_table
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_table_worker, args=(r, WORLD, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(WORLD)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    vt = value_table.ValueTable(device=dev)
+    for batch in range(2):
+        vt.update_from_playout(ops.playout(3000 * WORLD, seed=23, gid0=batch * WORLD * 3000, device=dev))
+    want = dict(zip(vt.keys.cpu().numpy().tolist(), vt.values.cpu().numpy().tolist()))
+    union = {}
+    for _, k, v in got:
+        assert not (set(k.tolist()) & set(union))                 # shares are disjoint
+        union.update(zip(k.tolist(), v.tolist()))
+    assert union == want

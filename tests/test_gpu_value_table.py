@@ -1,6 +1,8 @@
-"""The order-dependent value table on a B200 vs a dict-based restatement of the
-reference's loop: __update_state_for_a_book + __update_state_map
-(progress_position_moves_learn.py:37-62) driven by oracle features.  Values must be BIT-identical."""
+"""The order-dependent value table on a B200.  Pinned twice: to vectors produced by
+EXECUTING the reference's own __update_state_for_a_book / __update_state_map
+(progress_position_moves_learn.py:37-62; tests/golden/value_table.json.gz, oracle/make_golden.py) and, on
+other games, to a dict-based restatement of that loop driven by oracle features.  Values must be
+BIT-identical."""
 import numpy as np
 import pytest
 import torch
@@ -27,6 +29,53 @@ def reference_table_update(oracle, table, ref, a=0.03, l=0.90):
                 new = float(value) * (l ** (L - t))
                 table[key] = new if cur == 0 else cur * (1 - a) + new * a
     return table
+
+
+def test_value_table_equals_what_the_reference_text_computes():
+    """golden: the reference's own update methods, run from their source text on the first 24 golden games
+    in two batches (the table carries over); the CUDA table must hold the same keys and the same bits"""
+    from conftest import load_golden
+    gold = load_golden("value_table.json.gz")
+    vt = value_table.ValueTable(device=DEV, a=gold['a'], lam=gold['l'])
+    for (lo, hi), want in zip(gold['batches'], gold['after']):
+        vt.update_from_playout(ops.playout(hi - lo, seed=gold['seed'], gid0=lo, device=DEV))
+        got = {':'.join(str(v) for v in k): val.hex() for k, val in vt.items().items()}
+        assert got == want
+
+
+def test_stable_radix_sort_and_owner_partition():
+    """othello_sort_records == a stable sort by key (order inside a key preserved), for ragged sizes and
+    heavy duplicates; othello_partition_records == a stable split by owner whose blocks add up"""
+    import ctypes
+    from subproc_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device=DEV); g.manual_seed(5)
+    vt = value_table.ValueTable(device=DEV)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    for n, distinct in ((1, 1), (4095, 7), (4097, 300), (200000 + 13, 1 << 40), (1 << 20, 1000)):
+        keys = torch.randint(1, distinct + 1, (n,), generator=g, device=DEV, dtype=torch.int64)
+        keys |= torch.randint(4, 65, (n,), generator=g, device=DEV, dtype=torch.int64) << 36       # disc count on top
+        vals = torch.arange(n, device=DEV, dtype=torch.float64)                                    # = original position
+        want_k, perm = torch.sort(keys, stable=True)
+        k2, v2 = vt.sort_records(keys.clone(), vals.clone())
+        assert torch.equal(k2, want_k) and torch.equal(v2, vals[perm])
+        for world in (2, 8):
+            ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+            counts = torch.zeros(world, dtype=torch.int64, device=DEV)
+            nbytes = int(L.othello_sort_workspace_bytes(n))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+            assert L.othello_partition_records(P(keys), P(vals), P(ko), P(vo), n, world, P(counts), P(ws), nbytes, None) == 0
+            c = counts.cpu().tolist()
+            assert sum(c) == n
+            at = 0
+            owners = {}
+            for r in range(world):
+                blk_k, blk_v = ko[at:at + c[r]], vo[at:at + c[r]]
+                assert bool((blk_v[1:] > blk_v[:-1]).all())                # order preserved inside an owner
+                assert torch.equal(keys[blk_v.long()], blk_k)
+                for k in blk_k[:50].cpu().tolist():
+                    assert owners.setdefault(k, r) == r                   # a key has one owner
+                at += c[r]
 
 
 def test_value_table_is_bit_identical_to_the_reference_loop(oracle):

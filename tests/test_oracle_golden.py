@@ -134,3 +134,28 @@ def test_learner_arithmetic(oracle):
     assert oracle.smooth(0.0, 5.5) == 5.5
     cur, new = 12.25, -3.5
     assert oracle.smooth(cur, new) == cur * (1 - 0.03) + new * 0.03
+
+
+def test_value_table_restatement_against_the_reference_text(oracle):
+    """tests/golden/value_table.json.gz was produced by EXECUTING the reference's own
+    __update_state_for_a_book / __update_state_map (progress_position_moves_learn.py:37-62, cut out of the
+    file by oracle/make_golden.py::reference_update_rule) on the first 24 golden games.  The oracle's
+    restatement of the target and the smoothing rule must land on the same bits."""
+    from conftest import load_golden
+    gold = load_golden("value_table.json.gz")
+    assert (gold['a'], gold['l'], gold['seed']) == (0.03, 0.90, 0)
+    table = {}
+    for (lo, hi), want in zip(gold['batches'], gold['after']):
+        ref = oracle.playout(gold['seed'], lo, hi - lo)
+        for g in range(hi - lo):
+            L = int(ref['nplies'][g])
+            b, w = ref['black'][:L + 1, g], ref['white'][:L + 1, g]
+            fo, fx = oracle.features(b, w, 1), oracle.features(b, w, 2)
+            nb = bin(int(ref['final_black'][g])).count('1')
+            nw = bin(int(ref['final_white'][g])).count('1')
+            for t in range(L, -1, -1):                               # terminal record first (replearn.py:37-38)
+                for feats, value in ((fo[t], nb - nw), (fx[t], nw - nb)):      # 'O' then 'X' (:44-47)
+                    key = ':'.join(str(int(v)) for v in feats)
+                    table[key] = oracle.smooth(table.get(key, 0.0), oracle.target(value, L - t))
+        assert set(table) == set(want)
+        assert all(table[k].hex() == want[k] for k in want)
