@@ -130,7 +130,7 @@ typedef struct {
     uint64_t *final_white;
     /* proc_black / proc_white may be different engines (GameRunner.__init__, game_runner.py:107-123): */
     int32_t  policy_white;        /* White's engine, or -1 = the same as `policy` (which is then both players') */
-    int32_t  reserved;
+    int32_t  games_per_warp;      /* greedy engine: games a warp plays, 8 / 16 / 32; anything else = chosen from n_games */
     const float *weights_white;   /* DEVICE float[4][10] for White's greedy engine, or NULL = `weights` */
     /* what GameRunner.play_a_game reports at the end of a game (game_runner.py:194-199) and
      * store_batch_stats sums over a batch (learn_base.py:70-88), accumulated (+=) over the games of

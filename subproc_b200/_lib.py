@@ -31,7 +31,7 @@ class PlayoutArgs(ctypes.Structure):
         ("weights", vp), ("t_max", i32), ("stride", i64),
         ("traj_black", vp), ("traj_white", vp), ("traj_move", vp),
         ("nplies", vp), ("final_black", vp), ("final_white", vp),
-        ("policy_white", i32), ("reserved", i32), ("weights_white", vp), ("totals", vp),
+        ("policy_white", i32), ("games_per_warp", i32), ("weights_white", vp), ("totals", vp),
     ]
 
 

@@ -60,8 +60,11 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     WarpScratch &ws = scratch[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
 
-    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    bool done = g >= a.n_games;                               // lanes past the batch only help evaluating
+    // a warp plays `gpw` games (one per lane, lanes >= gpw only help evaluating children): 32 for large
+    // batches; fewer for small ones, so that a batch of 2^16 games still fills every SM with warps
+    const int gpw = a.games_per_warp;
+    const int64_t g = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * gpw + lane;
+    bool done = lane >= gpw || g >= a.n_games;                // lanes without a game only help evaluating
     const int64_t gi = done ? 0 : g;
     const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
     const u64 w0 = a.white0 ? a.white0[gi] : OTHELLO_START_WHITE;
@@ -178,9 +181,14 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
 
 }  // namespace
 
-int ob_launch_greedy(const othello_playout_args &a, cudaStream_t s)
+int ob_launch_greedy(const othello_playout_args &args, cudaStream_t s)
 {
-    const unsigned blocks = ob_blocks(a.n_games, kThreads);
+    othello_playout_args a = args;
+    if (a.games_per_warp != 8 && a.games_per_warp != 16 && a.games_per_warp != 32) {
+        // auto: two waves of 6 CTAs x 4 warps on 148 SMs want ~7100 warps
+        a.games_per_warp = a.n_games >= 32 * 7104 ? 32 : a.n_games >= 16 * 7104 ? 16 : 8;
+    }
+    const unsigned blocks = ob_blocks(a.n_games, a.games_per_warp * kWarps);
     const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;
     if (a.traj_black) {
         if (subst) greedy_kernel<true, true><<<blocks, kThreads, 0, s>>>(a);

@@ -337,7 +337,7 @@ int othello_playout_host_async(othello_ctx *c, uint64_t seed, uint64_t gid0, int
         a.black0 = black0 ? d_b0 + c0 : nullptr; a.white0 = black0 ? d_w0 + c0 : nullptr; a.turn0 = turn0 ? d_t0 + c0 : nullptr;
         a.policy = policy; a.random_plies = random_plies; a.n_rand_black = n_rand_black; a.n_rand_white = n_rand_white;
         a.weights = weights ? d_wt : nullptr;
-        a.policy_white = policy_white; a.reserved = 0; a.weights_white = weights_white ? d_wt2 : nullptr;
+        a.policy_white = policy_white; a.games_per_warp = 0; a.weights_white = weights_white ? d_wt2 : nullptr;
         a.t_max = t_max; a.stride = n;
         a.traj_black = d_tb + c0; a.traj_white = d_tw + c0; a.traj_move = d_tm + c0;
         a.nplies = d_np + c0; a.final_black = d_fb + c0; a.final_white = d_fw + c0;

@@ -20,9 +20,11 @@
 //     such partial sum over as a 2^-40 fixed-point integer (two int64 words).
 // othello_learn_stats turns the integers into the [4][112] doubles the solver reads.
 //
-// Work split: one CTA = 32 games, warp w of 8 = plies [w * chunk, (w + 1) * chunk): a warp reads
-// coalesced 256-byte rows of the SoA trajectory (16 B per position), and 2^16 games already give
-// every SM ~60 resident warps.
+// Work split: one CTA = 32 games (one per lane), a unit of work = one block of kPlyBlock = 8 plies of
+// those games; the CTA's 8 warps take the blocks round robin.  A warp reads coalesced 256-byte rows of
+// the SoA trajectory (16 B per position, the next ply's rows are requested before the current ply is
+// worked on).  The blocks are fixed multiples of 8 plies, so the fp64 partial sums do not depend on the
+// launch geometry.
 #include "common.cuh"
 #include "fastboard.cuh"
 
@@ -32,6 +34,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = 32 * kWarps;
+constexpr int kPlyBlock = 8;                 // plies per unit of work (fixed: part of the definition of the fp64 sums)
 constexpr int kGames = 32;                   // games per CTA (one per lane)
 constexpr int kX = 10;                       // regressors incl. intercept
 constexpr int kFp = 10;                      // fp64 sums per shard: Xty[0..8] (Xty[9] is identically 0), sum y^2
@@ -88,7 +91,7 @@ __device__ __forceinline__ void fp_flush(const double (&f)[kFp], unsigned long l
     }
 }
 
-__global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__ traj_black,
+__global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restrict__ traj_black,
                                                          const u64 *__restrict__ traj_white,
                                                          const int32_t *__restrict__ nplies,
                                                          const u64 *__restrict__ final_black,
@@ -113,10 +116,7 @@ __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__
     }
     double value = 0.0;
     if (len >= 0) value = (double)(__popcll(final_black[g]) - __popcll(final_white[g]));   // value_for_black (:40-42)
-    const int chunk = (t_max + 1 + kWarps - 1) / kWarps;
-    const int t0 = warp * chunk;
-    int t1 = min(t0 + chunk, t_max + 1);
-    t1 = min(t1, __reduce_max_sync(kFull, len) + 1);          // positions 0..nplies are recorded
+    const int t_end = min(t_max, __reduce_max_sync(kFull, len)) + 1;     // positions 0..nplies are recorded
 
     Gram gram;
     gram.clear();
@@ -127,64 +127,73 @@ __global__ void __launch_bounds__(kThreads) learn_kernel(const u64 *__restrict__
     int mine = -1;                                            // shard of the lane's fp64 partial sums
     unsigned char *stage_b = (unsigned char *)&stage[warp][0][0][0];
     const int fr = lane >> 2, fc = lane & 3;                  // fragment row / column group of this lane
+    const u64 *pb = traj_black + g, *pw = traj_white + g;
 
-    for (int t = t0; t < t1; t++) {
-        const bool live = t <= len;
-        int x[2][kX - 1];
-        int shard = -1;
-        if (live) {
-            const u64 b = traj_black[(int64_t)t * stride + g], w = traj_white[(int64_t)t * stride + g];
-            shard = phase_row(__popcll(b | w));
-            obf::mobility_both(b, w, x[0][0], x[1][0]);
+    for (int t0 = warp * kPlyBlock; t0 < t_end; t0 += kWarps * kPlyBlock) {
+        const int t1 = min(t0 + kPlyBlock, t_end);
+        u64 nb = 0, nw = 0;
+        if (t0 <= len) { nb = pb[(int64_t)t0 * stride]; nw = pw[(int64_t)t0 * stride]; }
+        for (int t = t0; t < t1; t++) {
+            const bool live = t <= len;
+            const u64 b = nb, w = nw;
+            if (t + 1 < t1 && t + 1 <= len) { nb = pb[(int64_t)(t + 1) * stride]; nw = pw[(int64_t)(t + 1) * stride]; }
+            int x[2][kX - 1];
+            int shard = -1;
+            if (live) {
+                shard = phase_row(__popcll(b | w));
+                obf::mobility_both(b, w, x[0][0], x[1][0]);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                x[0][1 + k] = __popcll(b & kClassMask[k]);
-                x[1][1 + k] = __popcll(w & kClassMask[k]);
+                for (int k = 0; k < 8; k++) {
+                    x[0][1 + k] = __popcll(b & kClassMask[k]);
+                    x[1][1 + k] = __popcll(w & kClassMask[k]);
+                }
+                if (shard != mine) {
+                    if (mine >= 0) fp_flush(f, s_fp, mine);
+#pragma unroll
+                    for (int k = 0; k < kFp; k++) f[k] = 0.0;
+                    mine = shard;
+                }
+                const double y = value * __ldg(decay + (len - t));                        // * l ** turn_left (:55)
+                // White's target is the negative of Black's (value_for_white, :42); the intercept terms cancel
+#pragma unroll
+                for (int k = 0; k < kX - 1; k++) f[k] += (double)(x[0][k] - x[1][k]) * y;
+                f[kFp - 1] += 2.0 * (y * y);
             }
-            if (shard != mine) {
-                if (mine >= 0) fp_flush(f, s_fp, mine);
+            // X^T X of the warp's positions, shard by shard (one shard unless games with passes straddle a boundary)
+            unsigned todo = __ballot_sync(kFull, live);
+            while (todo) {
+                const int s = __shfl_sync(kFull, shard, __ffs(todo) - 1);
+                const unsigned grp = __ballot_sync(kFull, live && shard == s);
+                todo &= ~grp;
+                if (s != cur) {
+                    if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
+                    gram.clear();
+                    cur = s;
+                }
+                const bool in = (grp >> lane) & 1u;
 #pragma unroll
-                for (int k = 0; k < kFp; k++) f[k] = 0.0;
-                mine = shard;
+                for (int side = 0; side < 2; side++) {
+#pragma unroll
+                    for (int k = 0; k < kX - 1; k++) stage_b[(side * kX + k) * 32 + lane] = (unsigned char)(in ? x[side][k] : 0);
+                    stage_b[(side * kX + kX - 1) * 32 + lane] = in ? 1 : 0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const unsigned a0 = stage[warp][side][fr][fc], a2 = stage[warp][side][fr][4 + fc];
+                    const unsigned a1 = fr < 2 ? stage[warp][side][8 + fr][fc] : 0u;
+                    const unsigned a3 = fr < 2 ? stage[warp][side][8 + fr][4 + fc] : 0u;
+                    mma_s8(gram.lo, a0, a1, a2, a3, a0, a2);       // columns = features 0..7
+                    mma_s8(gram.hi, a0, a1, a2, a3, a1, a3);       // columns = features 8, 9
+                }
+                __syncwarp();
             }
-            const double y = value * __ldg(decay + (len - t));                        // * l ** turn_left (:55)
-            // White's target is the negative of Black's (value_for_white, :42); the intercept terms cancel
-#pragma unroll
-            for (int k = 0; k < kX - 1; k++) f[k] += (double)(x[0][k] - x[1][k]) * y;
-            f[kFp - 1] += 2.0 * (y * y);
         }
-        // X^T X of the warp's positions, shard by shard (one shard unless games with passes straddle a boundary)
-        unsigned todo = __ballot_sync(kFull, live);
-        while (todo) {
-            const int s = __shfl_sync(kFull, shard, __ffs(todo) - 1);
-            const unsigned grp = __ballot_sync(kFull, live && shard == s);
-            todo &= ~grp;
-            if (s != cur) {
-                if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
-                gram.clear();
-                cur = s;
-            }
-            const bool in = (grp >> lane) & 1u;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-#pragma unroll
-                for (int k = 0; k < kX - 1; k++) stage_b[(side * kX + k) * 32 + lane] = (unsigned char)(in ? x[side][k] : 0);
-                stage_b[(side * kX + kX - 1) * 32 + lane] = in ? 1 : 0;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                const unsigned a0 = stage[warp][side][fr][fc], a2 = stage[warp][side][fr][4 + fc];
-                const unsigned a1 = fr < 2 ? stage[warp][side][8 + fr][fc] : 0u;
-                const unsigned a3 = fr < 2 ? stage[warp][side][8 + fr][4 + fc] : 0u;
-                mma_s8(gram.lo, a0, a1, a2, a3, a0, a2);       // columns = features 0..7
-                mma_s8(gram.hi, a0, a1, a2, a3, a1, a3);       // columns = features 8, 9
-            }
-            __syncwarp();
-        }
+        // the end of a ply block closes the lane's fp64 partial sums: (game, block, shard) is the unit that is
+        // rounded to fixed point, whatever warp, CTA or GPU works on it
+        if (mine >= 0) { fp_flush(f, s_fp, mine); mine = -1; }
     }
     if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
-    if (mine >= 0) fp_flush(f, s_fp, mine);
     __syncthreads();
     for (int i = threadIdx.x; i < OTHELLO_PHASES * OTHELLO_ACC; i += kThreads) {
         const int s = i / OTHELLO_ACC, k = i % OTHELLO_ACC;
@@ -230,8 +239,8 @@ extern "C" int othello_learn_accumulate(const uint64_t *traj_black, const uint64
     OB_CHECK_ARGS(n_games >= 0 && t_max >= 0 && acc && decay);
     if (n_games == 0) return 0;
     OB_CHECK_ARGS(traj_black && traj_white && nplies && final_black && final_white && stride >= n_games);
-    // a warp's int32 Gram accumulators hold at most chunk * 32 positions * 2 sides * 64^2 < 2^31
-    OB_CHECK_ARGS(t_max < 8 * kWarps * 128);
+    // a warp's int32 Gram accumulators hold at most (t_max / 8 + 1) plies * 32 positions * 2 sides * 64^2 < 2^31
+    OB_CHECK_ARGS(t_max < 8 * 8000);
     const int64_t blocks = (n_games + kGames - 1) / kGames;
     OB_CHECK_ARGS(blocks <= 0x7fffffff);
     learn_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(

@@ -326,21 +326,30 @@ __global__ void __launch_bounds__(kSortThreads) table_apply_kernel(const u64 *__
             for (u64 h = slot_of(k, log2cap);; h = (h + 1) & mask)                  // keys of one batch are distinct: plain CAS claim
                 if (atomicCAS((unsigned long long *)&slot_keys[h], 0ull, (unsigned long long)k) == 0ull) { slot_idx[h] = (int32_t)di; break; }
         }
-        for (int64_t j = i;; j += 8) {                                              // the run starts at its head
-            double x[8];
-            bool same[8];
+        // where the run ends: gallop, then bisect, on the sorted keys (one load for a run of length one)
+        int64_t lo = i, hi = i + 1;                                                 // keys[lo] == k; the end is in (lo, hi]
+        for (int64_t step = 1; hi < n && keys[hi] == k; step <<= 1) { lo = hi; hi = lo + step < n ? lo + step : n; }
+        if (hi > n) hi = n;
+        while (hi - lo > 1) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (keys[mid] == k) lo = mid; else hi = mid;
+        }
+        const int64_t end = hi;                                                     // first record of the next key
+        // the recurrence is sequential by definition (:56-61); the loads are not: a block of 16 targets is
+        // requested while the previous block is being folded in
+        constexpr int kB = 16;
+        double x[kB];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                same[q] = j + q < n && keys[j + q] == k;
-                x[q] = same[q] ? __ldg(targets + j + q) : 0.0;
-            }
-            bool more = true;
+        for (int q = 0; q < kB; q++) x[q] = i + q < end ? __ldg(targets + i + q) : 0.0;
+        for (int64_t j = i; j < end; j += kB) {
+            double nx[kB];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (more && same[q]) v = smooth_step(v, x[q], keep, a);
-                else more = false;
-            }
-            if (!more) break;
+            for (int q = 0; q < kB; q++) nx[q] = j + kB + q < end ? __ldg(targets + j + kB + q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < kB; q++)
+                if (j + q < end) v = smooth_step(v, x[q], keep, a);
+#pragma unroll
+            for (int q = 0; q < kB; q++) x[q] = nx[q];
         }
         dense_values[di] = v;
     }

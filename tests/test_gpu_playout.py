@@ -178,3 +178,25 @@ def test_perft_parts_add_up_and_workspace_follows_depth(oracle):
     rc = L.othello_perft(ops.START_BLACK, ops.START_WHITE, 1, 9, ctypes.c_void_p(ws.data_ptr()), ws.numel(),
                          ctypes.byref(res), None)
     assert rc == -2
+
+
+def test_greedy_games_do_not_depend_on_games_per_warp(oracle):
+    """the greedy kernel's small-batch modes (8 / 16 games per warp, the other lanes only evaluate children)
+    play the same games as the 32-games-per-warp layout and as the oracle"""
+    w = torch.from_numpy(oracle.DEFAULT_WEIGHTS.astype(np.float32)).to(DEV)
+    n = 3000 + 7
+    ref = oracle.playout(19, 40, 600, policy=1, random_plies=6, n_rand_black=2, n_rand_white=1)
+    outs = []
+    for gpw in (32, 16, 8, 0):
+        tot = torch.zeros(4, dtype=torch.int64, device=DEV)
+        po = ops.playout(n, seed=19, gid0=40, device=DEV, policy=ops.POLICY_GREEDY, random_plies=6, n_rand_black=2,
+                         n_rand_white=1, weights=w, games_per_warp=gpw, totals=tot)
+        assert np.array_equal(po.nplies[:600].cpu().numpy(), ref['nplies'])
+        assert np.array_equal(ops.bits_numpy(po.final_black[:600]), ref['final_black'])
+        t = 30
+        live = ref['nplies'] > t
+        assert np.array_equal(ops.bits_numpy(po.black[t][:600])[live], ref['black'][t][live])
+        assert np.array_equal(po.move[t][:600].cpu().numpy()[live], ref['move'][t][live])
+        outs.append((po.nplies.clone(), po.final_black.clone(), po.final_white.clone(), tot))
+    for o in outs[1:]:
+        assert all(torch.equal(x, y) for x, y in zip(o, outs[0]))
