@@ -35,14 +35,17 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=SO):
+    """defines / out: experimental variants (tools/ab.sh); the product is the default build"""
+    if not force and not defines and out == SO and not stale():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd)
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else SO))

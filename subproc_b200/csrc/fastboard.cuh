@@ -95,9 +95,26 @@ OBF_HD Inter rev_inter(Inter v) { return Inter{brev32(v.b), brev32(v.a)}; }
 OBF_HD Inter iand(Inter x, Inter y) { return Inter{x.a & y.a, x.b & y.b}; }
 OBF_HD Inter ior(Inter x, Inter y) { return Inter{x.a | y.a, x.b | y.b}; }
 
+#if defined(__CUDACC__)
+// An integer 1 the compiler cannot see through: multiplying by it keeps an addition on the FMA pipe
+// (IMAD) instead of the saturated ALU pipe (IADD3 / SEL / LOP3).
+static __device__ __constant__ u32 kOpaqueOne = 1u;
+#endif
+
+// v >> 1.  A right shift is an ALU-pipe instruction (SHF); as the high half of v * 2^31 it is an IMAD.HI on
+// the FMA pipe (half rate, but that pipe has room while the ALU pipe is the one that binds).
+OBF_HD u32 shr1(u32 v)
+{
+#if defined(__CUDA_ARCH__) && defined(OBF_SHR_IMADHI)
+    return __umulhi(v, kOpaqueOne << 31);
+#else
+    return v >> 1;
+#endif
+}
+
 template <int D> OBF_HD Inter ishift(Inter v)        // D squares up (towards higher squares), D in {7, 8, 9}
 {
-    return D == 8 ? Inter{v.b << 8, v.a} : D == 9 ? Inter{v.b << 9, v.a << 1} : Inter{v.b << 7, v.a >> 1};
+    return D == 8 ? Inter{v.b << 8, v.a} : D == 9 ? Inter{v.b << 9, v.a << 1} : Inter{v.b << 7, shr1(v.a)};
 }
 template <int D> OBF_HD Inter ishift2(Inter v)       // 2 * D squares up
 {
@@ -192,10 +209,6 @@ OBF_HD u64 ray_flips(u64 x, u64 R, u64 own, u64 opp)
 }
 
 #if defined(__CUDACC__)
-// An integer 1 the compiler cannot see through: multiplying by it keeps an addition on the FMA pipe
-// (IMAD) instead of the saturated ALU pipe (IADD3 / SEL / LOP3).
-static __device__ __constant__ u32 kOpaqueOne = 1u;
-
 // acc += run when the ray is closed.  The flipped runs of the 8 rays are pairwise disjoint, so the
 // OR-accumulation of put() is an ADD; gated by a predicate and issued as IMAD it costs the ALU pipe
 // two instructions (OR of the two halves of `closed`, compare) instead of five.

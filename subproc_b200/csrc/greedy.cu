@@ -185,8 +185,7 @@ int ob_launch_greedy(const othello_playout_args &args, cudaStream_t s)
 {
     othello_playout_args a = args;
     if (a.games_per_warp != 8 && a.games_per_warp != 16 && a.games_per_warp != 32) {
-        // auto: two waves of 6 CTAs x 4 warps on 148 SMs want ~7100 warps
-        a.games_per_warp = a.n_games >= 32 * 7104 ? 32 : a.n_games >= 16 * 7104 ? 16 : 8;
+        a.games_per_warp = 32;
     }
     const unsigned blocks = ob_blocks(a.n_games, a.games_per_warp * kWarps);
     const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;

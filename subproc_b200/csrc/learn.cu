@@ -20,11 +20,10 @@
 //     such partial sum over as a 2^-40 fixed-point integer (two int64 words).
 // othello_learn_stats turns the integers into the [4][112] doubles the solver reads.
 //
-// Work split: one CTA = 32 games (one per lane), a unit of work = one block of kPlyBlock = 8 plies of
-// those games; the CTA's 8 warps take the blocks round robin.  A warp reads coalesced 256-byte rows of
-// the SoA trajectory (16 B per position, the next ply's rows are requested before the current ply is
-// worked on).  The blocks are fixed multiples of 8 plies, so the fp64 partial sums do not depend on the
-// launch geometry.
+// Work split: a unit of work = 32 games (one per lane) x one block of kPlyBlock = 8 plies; the units are
+// dealt round robin to the warps of a persistent grid.  A warp reads coalesced 256-byte rows of the SoA
+// trajectory (16 B per position, the next ply's rows are requested before the current ply is worked on).
+// The blocks are fixed multiples of 8 plies, so the fp64 partial sums do not depend on the launch geometry.
 #include "common.cuh"
 #include "fastboard.cuh"
 
@@ -66,71 +65,90 @@ struct Gram {                                // the warp's 16 x 16 accumulator: 
 // hand the upper triangle of the warp's accumulator to the CTA totals of `shard`; every needed entry
 // is held by exactly one lane (fragment layout of m16n8k32: c0/c1 = row lane/4, columns 2 * (lane % 4) + {0, 1};
 // c2/c3 = row lane/4 + 8)
-__device__ __forceinline__ void gram_flush(const Gram &g, unsigned (*s_xtx)[kPairs], int shard, int lane)
+__device__ __forceinline__ void gram_flush(const Gram &g, unsigned long long (*s_xtx)[kPairs], int shard, int lane)
 {
     const int r = lane >> 2, c = 2 * (lane & 3);
-    if (r <= c && g.lo[0]) atomicAdd(&s_xtx[shard][pair_index(r, c)], (unsigned)g.lo[0]);
-    if (r <= c + 1 && g.lo[1]) atomicAdd(&s_xtx[shard][pair_index(r, c + 1)], (unsigned)g.lo[1]);
+    if (r <= c && g.lo[0]) atomicAdd(&s_xtx[shard][pair_index(r, c)], (unsigned long long)g.lo[0]);
+    if (r <= c + 1 && g.lo[1]) atomicAdd(&s_xtx[shard][pair_index(r, c + 1)], (unsigned long long)g.lo[1]);
     if ((lane & 3) == 0) {                   // columns 8 and 9
-        if (g.hi[0]) atomicAdd(&s_xtx[shard][pair_index(r, 8)], (unsigned)g.hi[0]);
-        if (g.hi[1]) atomicAdd(&s_xtx[shard][pair_index(r, 9)], (unsigned)g.hi[1]);
-        if (r == 0 && g.hi[2]) atomicAdd(&s_xtx[shard][pair_index(8, 8)], (unsigned)g.hi[2]);
-        if (r <= 1 && g.hi[3]) atomicAdd(&s_xtx[shard][pair_index(8 + r, 9)], (unsigned)g.hi[3]);
+        if (g.hi[0]) atomicAdd(&s_xtx[shard][pair_index(r, 8)], (unsigned long long)g.hi[0]);
+        if (g.hi[1]) atomicAdd(&s_xtx[shard][pair_index(r, 9)], (unsigned long long)g.hi[1]);
+        if (r == 0 && g.hi[2]) atomicAdd(&s_xtx[shard][pair_index(8, 8)], (unsigned long long)g.hi[2]);
+        if (r <= 1 && g.hi[3]) atomicAdd(&s_xtx[shard][pair_index(8 + r, 9)], (unsigned long long)g.hi[3]);
     }
 }
 
-// a lane's fp64 partial sums of one (game, ply block, shard) -> 2^-40 fixed point, exact integer adds from here on
-__device__ __forceinline__ void fp_flush(const double (&f)[kFp], unsigned long long (*s_fp)[2 * kFp], int shard)
+// The lanes' fp64 partial sums of one (game, ply block, shard) -> 2^-40 fixed point, exact integer adds from
+// here on.  The 32 integers of a value are added over the warp first (three 21-bit limbs through the
+// warp-reduce instruction: no carries to lose), then lane k adds value k to the CTA totals: two shared
+// atomics per value per warp instead of 64 colliding ones.
+__device__ __forceinline__ void fp_flush(const double (&f)[kFp], bool in, unsigned long long (*s_fp)[2 * kFp], int shard, int lane)
 {
+    long long mine = 0;
 #pragma unroll
     for (int k = 0; k < kFp; k++) {
-        if (f[k] == 0.0) continue;
-        const long long q = __double2ll_rn(f[k] * kFixScale);
-        atomicAdd(&s_fp[shard][2 * k], (unsigned long long)(q >> 32));               // signed high part
-        atomicAdd(&s_fp[shard][2 * k + 1], (unsigned long long)(q & 0xffffffffll));  // unsigned low 32 bits
+        const long long q = in ? __double2ll_rn(f[k] * kFixScale) : 0ll;              // |q| < 2^60
+        const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(q & 0x1fffff));
+        const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((q >> 21) & 0x1fffff));
+        const int l2 = __reduce_add_sync(kFull, (int)(q >> 42));                       // signed top limb
+        const long long sum = (long long)l0 + ((long long)l1 << 21) + ((long long)l2 << 42);
+        if (lane == k) mine = sum;
+    }
+    if (lane < kFp && mine != 0) {
+        atomicAdd(&s_fp[shard][2 * lane], (unsigned long long)(mine >> 32));               // signed high part
+        atomicAdd(&s_fp[shard][2 * lane + 1], (unsigned long long)(mine & 0xffffffffll));  // unsigned low 32 bits
     }
 }
 
+// Persistent warps: the units of work -- (group of 32 games, block of 8 plies), group-major inside a
+// block index -- are dealt round robin to all warps of the grid, so every warp walks from the opening to the
+// endgame (its shard, and with it the Gram accumulator, changes three times) and all warps run out of work
+// together.
 __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restrict__ traj_black,
-                                                         const u64 *__restrict__ traj_white,
-                                                         const int32_t *__restrict__ nplies,
-                                                         const u64 *__restrict__ final_black,
-                                                         const u64 *__restrict__ final_white, int64_t n_games,
-                                                         int64_t stride, int t_max, const double *__restrict__ decay,
-                                                         unsigned long long *__restrict__ acc)
+                                                            const u64 *__restrict__ traj_white,
+                                                            const int32_t *__restrict__ nplies,
+                                                            const u64 *__restrict__ final_black,
+                                                            const u64 *__restrict__ final_white, int64_t n_games,
+                                                            int64_t stride, int t_max, const double *__restrict__ decay,
+                                                            unsigned long long *__restrict__ acc)
 {
-    __shared__ unsigned s_xtx[OTHELLO_PHASES][kPairs];
+    __shared__ unsigned long long s_xtx[OTHELLO_PHASES][kPairs];
     __shared__ unsigned long long s_fp[OTHELLO_PHASES][2 * kFp];
     // feature bytes of the warp's 32 positions, [side][feature][position]: the K-major operand of the Gram product
     __shared__ unsigned stage[kWarps][2][kX][8];
-    for (int i = threadIdx.x; i < OTHELLO_PHASES * kPairs; i += kThreads) (&s_xtx[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < OTHELLO_PHASES * kPairs; i += kThreads) (&s_xtx[0][0])[i] = 0ull;
     for (int i = threadIdx.x; i < OTHELLO_PHASES * 2 * kFp; i += kThreads) (&s_fp[0][0])[i] = 0ull;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * kGames + lane;
-    int len = -1;
-    if (g < n_games) {
-        len = nplies[g];
-        if (len > t_max) len = -1;                            // truncated games are skipped
-    }
-    double value = 0.0;
-    if (len >= 0) value = (double)(__popcll(final_black[g]) - __popcll(final_white[g]));   // value_for_black (:40-42)
-    const int t_end = min(t_max, __reduce_max_sync(kFull, len)) + 1;     // positions 0..nplies are recorded
+    const int64_t n_groups = (n_games + kGames - 1) / kGames;
+    const int64_t n_units = n_groups * (int64_t)((t_max + kPlyBlock) / kPlyBlock);       // blocks cover plies 0..t_max
+    const int64_t n_warps = (int64_t)gridDim.x * kWarps;
 
     Gram gram;
     gram.clear();
     int cur = -1;                                             // shard of the warp's Gram accumulator
-    double f[kFp];
-#pragma unroll
-    for (int k = 0; k < kFp; k++) f[k] = 0.0;
-    int mine = -1;                                            // shard of the lane's fp64 partial sums
+    int since_flush = 0;
     unsigned char *stage_b = (unsigned char *)&stage[warp][0][0][0];
     const int fr = lane >> 2, fc = lane & 3;                  // fragment row / column group of this lane
-    const u64 *pb = traj_black + g, *pw = traj_white + g;
 
-    for (int t0 = warp * kPlyBlock; t0 < t_end; t0 += kWarps * kPlyBlock) {
-        const int t1 = min(t0 + kPlyBlock, t_end);
+    for (int64_t u = (int64_t)blockIdx.x * kWarps + warp; u < n_units; u += n_warps) {
+        const int t0 = (int)(u / n_groups) * kPlyBlock;
+        const int64_t g = (u % n_groups) * kGames + lane;
+        int len = -1;
+        if (g < n_games) {
+            len = nplies[g];
+            if (len > t_max) len = -1;                        // truncated games are skipped
+        }
+        const int t1 = min(t0 + kPlyBlock, min(t_max, __reduce_max_sync(kFull, len)) + 1);   // positions 0..nplies are recorded
+        if (t0 >= t1) continue;
+        double value = 0.0;
+        if (t0 <= len) value = (double)(__popcll(final_black[g]) - __popcll(final_white[g]));   // value_for_black (:40-42)
+        const u64 *pb = traj_black + g, *pw = traj_white + g;
+        double f[kFp];
+#pragma unroll
+        for (int k = 0; k < kFp; k++) f[k] = 0.0;
+        int mine = -1;                                        // shard of the lane's fp64 partial sums
         u64 nb = 0, nw = 0;
         if (t0 <= len) { nb = pb[(int64_t)t0 * stride]; nw = pw[(int64_t)t0 * stride]; }
         for (int t = t0; t < t1; t++) {
@@ -138,6 +156,8 @@ __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restric
             const u64 b = nb, w = nw;
             if (t + 1 < t1 && t + 1 <= len) { nb = pb[(int64_t)(t + 1) * stride]; nw = pw[(int64_t)(t + 1) * stride]; }
             int x[2][kX - 1];
+#pragma unroll
+            for (int k = 0; k < kX - 1; k++) x[0][k] = x[1][k] = 0;
             int shard = -1;
             if (live) {
                 shard = phase_row(__popcll(b | w));
@@ -147,12 +167,24 @@ __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restric
                     x[0][1 + k] = __popcll(b & kClassMask[k]);
                     x[1][1 + k] = __popcll(w & kClassMask[k]);
                 }
-                if (shard != mine) {
-                    if (mine >= 0) fp_flush(f, s_fp, mine);
+            }
+            // a lane's shard changes at most once inside a block (8 plies < 16 discs): close its partial sums;
+            // the warp does it together (lanes that do not change contribute nothing)
+            const bool change = live && mine >= 0 && shard != mine;
+            if (__any_sync(kFull, change)) {
+                for (unsigned todo = __ballot_sync(kFull, change); todo;) {
+                    const int s = __shfl_sync(kFull, mine, __ffs(todo) - 1);
+                    const bool in = change && mine == s;
+                    todo &= ~__ballot_sync(kFull, in);
+                    fp_flush(f, in, s_fp, s, lane);
+                    if (in) {
 #pragma unroll
-                    for (int k = 0; k < kFp; k++) f[k] = 0.0;
-                    mine = shard;
+                        for (int k = 0; k < kFp; k++) f[k] = 0.0;
+                    }
                 }
+            }
+            if (live) {
+                mine = shard;
                 const double y = value * __ldg(decay + (len - t));                        // * l ** turn_left (:55)
                 // White's target is the negative of Black's (value_for_white, :42); the intercept terms cancel
 #pragma unroll
@@ -160,21 +192,25 @@ __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restric
                 f[kFp - 1] += 2.0 * (y * y);
             }
             // X^T X of the warp's positions, shard by shard (one shard unless games with passes straddle a boundary)
-            unsigned todo = __ballot_sync(kFull, live);
-            while (todo) {
+            const unsigned alive = __ballot_sync(kFull, live);
+            for (unsigned todo = alive; todo;) {
                 const int s = __shfl_sync(kFull, shard, __ffs(todo) - 1);
                 const unsigned grp = __ballot_sync(kFull, live && shard == s);
                 todo &= ~grp;
-                if (s != cur) {
+                if (s != cur || since_flush >= 4096) {        // (int32 accumulators: 4096 plies x 32 x 2 x 64^2 < 2^31)
                     if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
                     gram.clear();
                     cur = s;
+                    since_flush = 0;
                 }
-                const bool in = (grp >> lane) & 1u;
+                since_flush++;
+                const bool in = (grp >> lane) & 1u;           // (x is all zero for lanes that are not live)
+                const bool whole = grp == alive;              // the usual case: nothing to mask
 #pragma unroll
                 for (int side = 0; side < 2; side++) {
 #pragma unroll
-                    for (int k = 0; k < kX - 1; k++) stage_b[(side * kX + k) * 32 + lane] = (unsigned char)(in ? x[side][k] : 0);
+                    for (int k = 0; k < kX - 1; k++)
+                        stage_b[(side * kX + k) * 32 + lane] = (unsigned char)((whole || in) ? x[side][k] : 0);
                     stage_b[(side * kX + kX - 1) * 32 + lane] = in ? 1 : 0;
                 }
                 __syncwarp();
@@ -189,9 +225,14 @@ __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restric
                 __syncwarp();
             }
         }
-        // the end of a ply block closes the lane's fp64 partial sums: (game, block, shard) is the unit that is
+        // the end of a ply block closes the lanes' fp64 partial sums: (game, block, shard) is the unit that is
         // rounded to fixed point, whatever warp, CTA or GPU works on it
-        if (mine >= 0) { fp_flush(f, s_fp, mine); mine = -1; }
+        for (unsigned todo = __ballot_sync(kFull, mine >= 0); todo;) {
+            const int s = __shfl_sync(kFull, mine, __ffs(todo) - 1);
+            const bool in = mine == s;
+            todo &= ~__ballot_sync(kFull, in);
+            fp_flush(f, in, s_fp, s, lane);
+        }
     }
     if (cur >= 0) gram_flush(gram, s_xtx, cur, lane);
     __syncthreads();
@@ -239,11 +280,14 @@ extern "C" int othello_learn_accumulate(const uint64_t *traj_black, const uint64
     OB_CHECK_ARGS(n_games >= 0 && t_max >= 0 && acc && decay);
     if (n_games == 0) return 0;
     OB_CHECK_ARGS(traj_black && traj_white && nplies && final_black && final_white && stride >= n_games);
-    // a warp's int32 Gram accumulators hold at most (t_max / 8 + 1) plies * 32 positions * 2 sides * 64^2 < 2^31
-    OB_CHECK_ARGS(t_max < 8 * 8000);
-    const int64_t blocks = (n_games + kGames - 1) / kGames;
-    OB_CHECK_ARGS(blocks <= 0x7fffffff);
-    learn_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+    const int64_t units = ((n_games + kGames - 1) / kGames) * (int64_t)((t_max + kPlyBlock) / kPlyBlock);
+    int dev = 0, sms = 148;
+    OB_CUDA(cudaGetDevice(&dev));
+    OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t resident = (int64_t)sms * 3;               // persistent: one wave of CTAs (3 per SM at 80 registers)
+    const int64_t want = (units + kWarps - 1) / kWarps;
+    const unsigned blocks = (unsigned)(want < resident ? want : resident);
+    learn_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
         (const u64 *)traj_black, (const u64 *)traj_white, nplies, (const u64 *)final_black, (const u64 *)final_white,
         n_games, stride, t_max, decay, (unsigned long long *)acc);
     return ob_launch_status();

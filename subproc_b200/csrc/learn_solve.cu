@@ -6,8 +6,8 @@
 // as the reference calls it (progress_position_moves_learn.py:167-181): centre the normal equations,
 // minimum-norm solution on the centred 9x9 Gram matrix (constant columns get coefficient 0), intercept,
 // RMSE and R^2 on the same statistics, then `coef * 127 / max|coef|` (:180-181) and int() truncation
-// toward zero (:200).  One warp per shard; the symmetric eigen-decomposition is cyclic Jacobi in fp64
-// (9x9: a dozen sweeps), rotations applied by 9 lanes in parallel.
+// toward zero (:200).  One warp per shard; the symmetric eigen-decomposition is parallel-order cyclic
+// Jacobi in fp64 (9x9: 9 rounds of 4 disjoint rotations per sweep, a handful of sweeps).
 #include "common.cuh"
 
 namespace {
@@ -54,39 +54,55 @@ __global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ st
     __syncwarp();
     double tr = 0.0;
     for (int j = 0; j < kN; j++) tr += A[j][j];                  // invariant under the rotations
+    // Parallel-order cyclic Jacobi: a sweep is 9 rounds of 4 rotations in disjoint planes (round-robin
+    // pairing of 9 indices + one bye), so the four (c, s) of a round are computed together from the current
+    // matrix and A <- J^T A J is applied as one column pass (lane = row) and one row pass (lane = column).
+    __shared__ double rc[4], rs[4];
+    __shared__ int rp[4], rq[4];
     for (int sweep = 0; sweep < kSweeps; sweep++) {
         double off = 0.0;
         for (int p = 0; p < kN; p++) for (int q = p + 1; q < kN; q++) off += A[p][q] * A[p][q];
-        if (off <= 1e-34 * tr * tr) break;                      // off-diagonal mass below fp64 resolution of the spectrum
-        for (int p = 0; p < kN - 1; p++) {
-            for (int q = p + 1; q < kN; q++) {
+        if (off <= 1e-32 * tr * tr) break;                      // off-diagonal mass below fp64 resolution of the spectrum
+        for (int round = 0; round < kN; round++) {
+            if (lane < 4) {
+                // circle method on 10 slots (slot 9 = bye): pairs (round + k, round - k) mod 9 skip the bye
+                int p = (round + lane + 1) % kN, q = (round + kN - lane - 1) % kN;
+                if (p > q) { const int t = p; p = q; q = t; }
                 const double apq = A[p][q];
-                if (apq == 0.0) continue;                       // warp-uniform: every lane reads the same value
-                const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
-                const double app = A[p][p], aqq = A[q][q];
-                double akp = 0.0, akq = 0.0, vkp = 0.0, vkq = 0.0;
-                if (lane < kN) {
-                    akp = A[lane][p]; akq = A[lane][q];
-                    vkp = V[lane][p]; vkq = V[lane][q];
+                double c = 1.0, sn = 0.0;
+                if (apq != 0.0) {
+                    const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    sn = t * c;
                 }
-                __syncwarp();
-                if (lane < kN) {
-                    if (lane != p && lane != q) {
-                        const double np_ = c * akp - sn * akq, nq_ = sn * akp + c * akq;
-                        A[lane][p] = np_; A[p][lane] = np_;
-                        A[lane][q] = nq_; A[q][lane] = nq_;
-                    }
-                    V[lane][p] = c * vkp - sn * vkq;
-                    V[lane][q] = sn * vkp + c * vkq;
-                }
-                if (lane == 0) {
-                    A[p][p] = app - t * apq; A[q][q] = aqq + t * apq;
-                    A[p][q] = 0.0; A[q][p] = 0.0;
-                }
-                __syncwarp();
+                rp[lane] = p; rq[lane] = q; rc[lane] = c; rs[lane] = sn;
             }
+            __syncwarp();
+            if (lane < kN) {                                    // columns p, q of row `lane`, of A and of V
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = rp[k], q = rq[k];
+                    const double c = rc[k], sn = rs[k];
+                    const double ap = A[lane][p], aq = A[lane][q];
+                    A[lane][p] = c * ap - sn * aq; A[lane][q] = sn * ap + c * aq;
+                    const double vp = V[lane][p], vq = V[lane][q];
+                    V[lane][p] = c * vp - sn * vq; V[lane][q] = sn * vp + c * vq;
+                }
+            }
+            __syncwarp();
+            if (lane < kN) {                                    // rows p, q of column `lane`
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = rp[k], q = rq[k];
+                    const double c = rc[k], sn = rs[k];
+                    const double ap = A[p][lane], aq = A[q][lane];
+                    A[p][lane] = c * ap - sn * aq; A[q][lane] = sn * ap + c * aq;
+                }
+            }
+            __syncwarp();
+            if (lane < 4) { A[rp[lane]][rq[lane]] = 0.0; A[rq[lane]][rp[lane]] = 0.0; }   // annihilated exactly
+            __syncwarp();
         }
     }
     double lmax = 0.0;

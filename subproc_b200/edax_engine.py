@@ -54,7 +54,7 @@ class Backend(object):
             key = (self.seed * 1000003 + self.games * 7919 + int(self.b.nturn)) & 0xFFFFFFFF
             x, y = legal[key % len(legal)] if self.policy == 'random' else legal[0]
             return self.b.handstr_from_coord(x, y).upper()
-        _, dev = self.b._ops()
+        dev = torch.device("cuda", self.b._ctx_index())
         own, opp = self.b._pair(self.b.turn)
         n = len(legal)
         sq = torch.tensor([x + 8 * y for x, y in legal], dtype=torch.uint8, device=dev)

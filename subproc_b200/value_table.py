@@ -59,6 +59,7 @@ class ValueTable(object):
         self._slot_idx = torch.zeros(1 << self._log2cap, dtype=torch.int32, device=self.device)
         self._counters = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._ws = {}
+        self.timings = None                                    # set to a list to collect CUDA events of update()
 
     def __len__(self):
         return self.n
@@ -148,19 +149,31 @@ class ValueTable(object):
         if n == 0:
             return
         L = _lib.lib()
+        tm = self.timings
+        ev = (lambda: None) if tm is None else (lambda: tm.append(self._event()))
+        ev()
         self.sort_records(keys, targets)
+        ev()
         nbytes = int(L.othello_table_workspace_bytes(n))
         ws = self._scratch("table", nbytes)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(L.othello_table_probe(P(keys), n, P(self._slot_keys), P(self._slot_idx), self._log2cap, P(ws), nbytes,
                                              P(self._counters), self._stream()), "othello_table_probe")
+            ev()
             n_new = int(self._counters[1].item())                 # the one host round trip of an update: sizing
             self._reserve(self.n + n_new)
+            ev()
             _lib.check(L.othello_table_apply(P(keys), P(targets), n, self.a, P(self._slot_keys), P(self._slot_idx),
                                              self._log2cap, P(self._keys), P(self._values), self.n, P(ws), self._stream()),
                        "othello_table_apply")
+            ev()
         self.n += n_new
+
+    def _event(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.device))
+        return e
 
     def update_from_playout(self, po):
         keys, targets = self.records_from_playout(po)

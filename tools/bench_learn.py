@@ -27,6 +27,8 @@ acc = torch.zeros((4, learner.N_ACC), dtype=torch.int64, device=dev)
 stats = torch.empty((4, 112), dtype=torch.float64, device=dev)
 out = {"games": G, "positions": po.total_positions() + G}
 out["greedy_playout_ms"] = ev(lambda: ops.playout(G, seed=3, gid0=0, device=dev, policy=ops.POLICY_GREEDY, random_plies=10, weights=w, out=po))
+for gpw in (32, 16, 8):
+    out["greedy_playout_gpw%d_ms" % gpw] = ev(lambda: ops.playout(G, seed=3, gid0=0, device=dev, policy=ops.POLICY_GREEDY, random_plies=10, weights=w, out=po, games_per_warp=gpw))
 out["learn_accumulate_ms"] = ev(lambda: ops.learn_accumulate(po, acc=acc))
 out["learn_positions_per_s"] = out["positions"] / out["learn_accumulate_ms"] * 1e3
 out["learn_stats_ms"] = ev(lambda: ops.learn_stats(acc, out=stats))

@@ -34,12 +34,17 @@ _, out["torch_sort_ms"] = ev(lambda: torch.sort(keys, stable=True))
 sk, st = vt.sort_records(keys.clone(), targets.clone())
 u, c = torch.unique_consecutive(sk, return_counts=True)
 out["distinct_keys"], out["longest_run"] = int(u.numel()), int(c.max())
-for label in ("first_update", "second_update"):                      # second: every key already in the table
+for label in ("first_update", "second_update", "third_update"):      # second: every key already in the table
     k2, t2 = keys.clone(), targets.clone()
+    vt.timings = []
     torch.cuda.synchronize(); t0 = time.perf_counter()
     vt.update(k2, t2)
     torch.cuda.synchronize()
     out[label + "_ms"] = 1e3 * (time.perf_counter() - t0)
+    e = vt.timings
+    out[label + "_phases_ms"] = dict(zip(("sort", "probe", "reserve", "apply"),
+                                         [round(e[i].elapsed_time(e[i + 1]), 3) for i in range(4)]))
+    vt.timings = None
 # whole update incl. the records kernel, wall clock
 vt2 = value_table.ValueTable(device=dev)
 vt2.update_from_playout(po)
