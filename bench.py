@@ -440,34 +440,60 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm: value ---------------------------------------------------------
-    po = ops.playout(G, seed=1, gid0=0, device=dev, t_max=T_MAX)          # allocates the 2 GB trajectory once
-    nplies_steps = [torch.empty(G, dtype=torch.int32, device=dev) for _ in range(K)]
+    # K launches of G games each.  Consecutive launches alternate over two streams (each with its own 2 GB
+    # trajectory buffer), so the thinning tail of one launch runs under the head of the next -- what any
+    # caller that streams batches does, and what the host-buffer path below does with its chunks.
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    pos = [ops.playout(G, seed=1, gid0=0, device=dev, t_max=T_MAX) for _ in range(2)]
+    tot = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    po = pos[0]
     gid_base = rank * (W + K) * G * 2
 
-    def one_step(i, nplies_out=None):
-        if nplies_out is not None:
-            po.nplies = nplies_out
-        ops.playout(G, seed=1, gid0=gid_base + i * G, device=dev, t_max=T_MAX, out=po)
+    def one_step(i, count):
+        k = i % 2
+        with torch.cuda.stream(streams[k]):
+            ops.playout(G, seed=1, gid0=gid_base + i * G, device=dev, t_max=T_MAX, out=pos[k],
+                        totals=tot[k] if count else None)
 
+    torch.cuda.synchronize()
     for i in range(W):
-        one_step(i)
+        one_step(i, False)
+    torch.cuda.synchronize()
     int_peak_alu = ops.int32_peak(dev)                                     # ALU pipe alone (LOP3/SHF), lane-ops/s
     int_peak = ops.int32_peak(dev, dual=True)                              # ALU + FMA pipes (LOP3 + IMAD): the integer ceiling
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    evs[0].record()
+    cur = torch.cuda.current_stream(dev)
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_start.record(cur)
+    for st in streams:
+        st.wait_event(ev_start)
     for i in range(K):
-        one_step(W + i, nplies_steps[i])
-        evs[i + 1].record()
+        one_step(W + i, True)
+        evs[i].record(streams[i % 2])
+    for st in streams:
+        cur.wait_stream(st)
+    ev_end.record(cur)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
-    total_ms = evs[0].elapsed_time(evs[K])
-    positions = sum(int(t.sum(dtype=torch.int64).item()) for t in nplies_steps)
+    # time a launch spends in its stream (launches of the two streams overlap, so these add up to more than the total)
+    step_ms = [(ev_start if i < 2 else evs[i - 2]).elapsed_time(evs[i]) for i in range(K)]
+    total_ms = ev_start.elapsed_time(ev_end)
+    positions = int(tot[0][0].item()) + int(tot[1][0].item())
     games = K * G
+    # one launch alone (nothing else on the GPU): the duration the ncu launch list is compared with
+    alone_ms = []
+    for i in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        ops.playout(G, seed=1, gid0=gid_base + (W + K + i) * G, device=dev, t_max=T_MAX, out=po)
+        e1.record()
+        e1.synchronize()
+        alone_ms.append(e0.elapsed_time(e1))
 
     # ---- the batch API on explicit positions: othello_step (put_s + game-over check) on synthetic
     # random-opening positions = the positions of this launch after 10 random plies, their next move
@@ -509,7 +535,7 @@ def run_b200_arm(args):
     h_t0 = pin(G, torch.uint8).fill_(ops.BLACK)
     h_out = [(pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64), pin(4, torch.int64)) for _ in range(2)]
     P = lambda t: ctypes.c_void_p(t.data_ptr())
-    e2e_gid = [gid_base + (W + K) * G]
+    e2e_gid = [gid_base + (W + K + 3) * G]
 
     def e2e_run(steps):
         """issue step i+1, then collect step i; returns the positions played (from the batch totals)"""
@@ -572,15 +598,30 @@ def run_b200_arm(args):
     if rank == 0:
         value = positions / (total_ms * 1e-3)
         hbm_peak, hbm_src = measured_peaks()
-        # the dominant (only) kernel of a step is playout_kernel<false,false,true>: per launch
-        kern_ms = sum(step_ms) / K
+        # the dominant (only) kernel of a step is playout_kernel<traj, uniform>; with two launches in flight the
+        # time a launch costs is the timed region divided by the launches in it
+        kern_ms = total_ms / K
         pos_per_launch = positions / (K * n_gpus)
         achieved_ops = pos_per_launch * LANE_OPS_PER_POSITION / (kern_ms * 1e-3)
         achieved_gbs = pos_per_launch * BYTES_PER_POSITION / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "playout_traffic.json")
+        # what ncu measured on one launch of this kernel (profiles/playout_kernel_costs.json, written by
+        # tools/kernel_costs.py from the committed ncu summary): DRAM traffic, executed instructions, pipe utilisation
+        traffic, executed = None, None
+        tp = os.path.join(ROOT, "profiles", "playout_kernel_costs.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            kc = json.load(open(tp))
+            traffic = kc.get("dram_bytes_per_launch")
+            live_rate = pos_per_launch / kern_ms                       # positions per ms, this run
+            scale = live_rate / kc["positions_per_ms_under_ncu"]
+            executed = {
+                "source": "profiles/playout_kernel_costs.json (ncu --set full of one launch: %s)" % kc["source"],
+                "thread_inst_per_position": kc["thread_inst_per_position"],
+                "active_lanes_per_inst": kc["active_lanes_per_inst"],
+                "alu_pipe_pct_ncu": kc["alu_pipe_pct"], "fmaheavy_pipe_pct_ncu": kc["fmaheavy_pipe_pct"],
+                "xu_pipe_pct_ncu": kc["xu_pipe_pct"], "issue_slot_pct_ncu": kc["issue_slot_pct"],
+                "alu_pipe_frac_at_this_runs_rate": kc["alu_pipe_pct"] / 100.0 * scale,
+                "note": "utilisation of the binding pipe (integer ALU) = the ncu figure scaled by this run's "
+                        "positions/s over the profiled launch's (the instructions per position are a constant of the kernel)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -594,11 +635,20 @@ def run_b200_arm(args):
                        "parallelism": "games sharded over %d GPU(s), no data-path collective" % n_gpus},
             "roofline": {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tlane-op/s", "frac": achieved_ops / int_peak, "traffic": traffic,
+                         "frac_definition": "ALGORITHM-normalised throughput, not a utilisation: positions/s x the canonical "
+                                            "512 lane-ops of 8-direction Kogge-Stone (SURVEY.md 8d) over the measured "
+                                            "LOP3+IMAD dual-issue peak; the kernel executes fewer instructions than the "
+                                            "canonical count, so the hardware truth is `executed` (ncu pipe utilisation)",
+                         "executed": executed,
                          "peak_source": "csrc/peak.cu, measured in this run: LOP3 + IMAD co-issued on the ALU and FMA "
                                         "pipes (the two pipes that execute 32-bit integer lane-ops)",
                          "peak_alu_pipe_only": int_peak_alu / 1e12, "frac_alu_pipe_only": achieved_ops / int_peak_alu,
                          "algorithmic": "%d INT32 lane-ops per position-step (SURVEY.md 8d)" % LANE_OPS_PER_POSITION,
                          "kernel": "playout_kernel<random,traj>", "kernel_ms": kern_ms,
+                         "kernel_ms_definition": "timed region / launches (consecutive launches alternate over two "
+                                                 "streams); a launch alone on the GPU takes kernel_alone_ms, and "
+                                                 "spends kernel_in_stream_ms in its stream when two are in flight",
+                         "kernel_alone_ms": min(alone_ms), "kernel_in_stream_ms": sum(step_ms) / K,
                          "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic": "%d B written per position" % BYTES_PER_POSITION}},

@@ -223,16 +223,17 @@ int othello_partition_records(const uint64_t *keys, const double *values, uint64
  *   othello_table_probe: marks the heads of the runs of equal keys and looks them up; counters[1] (DEVICE
  *     int64[2]) = number of keys the batch adds.  workspace: DEVICE, >= othello_table_workspace_bytes(n),
  *     handed unchanged to othello_table_apply.
- *   othello_table_apply: every run is walked in order by one thread, V = new if V == 0 else V*(1-a) + new*a
- *     in fp64 with the reference's rounding (no fused multiply-add), from the stored value (0 for a new
- *     key: `set(key, 0)`, :52-53).  New keys are appended to the dense arrays at n_before.. in key order and
- *     entered into the hash; needs 2 * (n_before + new) <= 2^log2_capacity. */
+ *   othello_table_apply: new keys are appended to the dense arrays at n_before.. in key order, entered into
+ *     the hash and start from 0 (`set(key, 0)`, :52-53); then every run is folded into its value in update
+ *     order, V = new if V == 0 else V*(1-a) + new*a in fp64 with the reference's rounding (no fused
+ *     multiply-add) -- short runs by one thread each, long runs (>= 128 records) by one warp each.  Needs
+ *     2 * (n_before + new) <= 2^log2_capacity <= 2^30. */
 int64_t othello_table_workspace_bytes(int64_t n);
 int othello_table_probe(const uint64_t *sorted_keys, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
                         int32_t log2_capacity, void *workspace, int64_t workspace_bytes, int64_t *counters, void *stream);
 int othello_table_apply(const uint64_t *sorted_keys, const double *sorted_targets, int64_t n, double a,
                         uint64_t *slot_keys, int32_t *slot_idx, int32_t log2_capacity, uint64_t *dense_keys,
-                        double *dense_values, int64_t n_before, const void *workspace, void *stream);
+                        double *dense_values, int64_t n_before, void *workspace, void *stream);
 /* (re)build the hash from dense_keys[0..n) (slot arrays zeroed by the caller); key -> dense index or -1 */
 int othello_table_rehash(const uint64_t *dense_keys, int64_t n, uint64_t *slot_keys, int32_t *slot_idx,
                          int32_t log2_capacity, void *stream);

@@ -79,24 +79,29 @@ __device__ __forceinline__ void gram_flush(const Gram &g, unsigned long long (*s
 }
 
 // The lanes' fp64 partial sums of one (game, ply block, shard) -> 2^-40 fixed point, exact integer adds from
-// here on.  The 32 integers of a value are added over the warp first (three 21-bit limbs through the
-// warp-reduce instruction: no carries to lose), then lane k adds value k to the CTA totals: two shared
-// atomics per value per warp instead of 64 colliding ones.
+// here on.  Every game's integer q is split into its signed high word and unsigned low 32 bits, and the two
+// are summed separately all the way (warp, CTA, grid, ranks): the pair of totals is then the same whatever
+// the grouping.  The 32 integers of a warp are added through the warp-reduce instruction in 16-bit limbs (no
+// carries to lose), then lane k adds value k to the CTA totals: two shared atomics per value per warp.
 __device__ __forceinline__ void fp_flush(const double (&f)[kFp], bool in, unsigned long long (*s_fp)[2 * kFp], int shard, int lane)
 {
-    long long mine = 0;
+    long long hi = 0;
+    unsigned long long lo = 0;
 #pragma unroll
     for (int k = 0; k < kFp; k++) {
         const long long q = in ? __double2ll_rn(f[k] * kFixScale) : 0ll;              // |q| < 2^60
-        const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(q & 0x1fffff));
-        const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((q >> 21) & 0x1fffff));
-        const int l2 = __reduce_add_sync(kFull, (int)(q >> 42));                       // signed top limb
-        const long long sum = (long long)l0 + ((long long)l1 << 21) + ((long long)l2 << 42);
-        if (lane == k) mine = sum;
+        const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(q & 0xffff));
+        const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((q >> 16) & 0xffff));
+        const unsigned l2 = __reduce_add_sync(kFull, (unsigned)((q >> 32) & 0xffff));
+        const int l3 = __reduce_add_sync(kFull, (int)(q >> 48));                       // signed top limb
+        if (lane == k) {
+            lo = (unsigned long long)l0 + ((unsigned long long)l1 << 16);              // = sum of the lanes' low words
+            hi = (long long)l2 + ((long long)l3 << 16);                                // = sum of the lanes' high words
+        }
     }
-    if (lane < kFp && mine != 0) {
-        atomicAdd(&s_fp[shard][2 * lane], (unsigned long long)(mine >> 32));               // signed high part
-        atomicAdd(&s_fp[shard][2 * lane + 1], (unsigned long long)(mine & 0xffffffffll));  // unsigned low 32 bits
+    if (lane < kFp) {
+        if (hi) atomicAdd(&s_fp[shard][2 * lane], (unsigned long long)hi);
+        if (lo) atomicAdd(&s_fp[shard][2 * lane + 1], lo);
     }
 }
 

@@ -237,12 +237,29 @@ __device__ __forceinline__ int table_find(u64 key, const u64 *slot_keys, const i
     }
 }
 
-// pass 1 over the sorted records: which records start a run (a "head"), which heads are new keys;
-// tag[i] = dense index of the key (head, known), -1 (head, new), -2 (not a head); new heads per tile -> tile_new
+// ---- applying a sorted batch --------------------------------------------------------------------------
+// probe : which records start a run of equal keys (a "head"), which heads are new keys, which runs are long
+// scan  : new heads per tile -> exclusive prefix (+ the total, which sizes the table on the host)
+// assign: new keys get dense indices in sorted-key order (the table's layout does not depend on scheduling),
+//         are entered into the hash, and start from 0 (`if not exists: set(key, 0)`, :52-53)
+// apply : every run is folded into its value in update order (:56-61).  Short runs: one thread per head, a
+//         plain loop.  Long runs (the opening positions are visited by every game): one warp per run, 32 targets
+//         per coalesced load, the recurrence evaluated by all lanes in step.
+constexpr int kLongRun = 128;                        // runs of at least this many records take the warp path
+constexpr int kLongFlag = 1 << 30;                   // tag bit: head of a long run
+constexpr int kLongBlocks = 64;                      // CTAs of the apply launch that serve the long runs
+
+struct TableCtl {
+    unsigned n_long;                                 // long runs found by the probe
+    unsigned next_long;                              // work cursor of the apply kernel
+};
+
+// tag[i] = -2: not a head; head of a known key: its dense index (| kLongFlag); head of a new key: -1 (short), -3 (long)
 __global__ void __launch_bounds__(kSortThreads) table_probe_kernel(const u64 *__restrict__ keys, int64_t n,
                                                                    const u64 *__restrict__ slot_keys,
                                                                    const int32_t *__restrict__ slot_idx, int log2cap,
-                                                                   int32_t *__restrict__ tag, unsigned *__restrict__ tile_new)
+                                                                   int32_t *__restrict__ tag, unsigned *__restrict__ tile_new,
+                                                                   int32_t *__restrict__ long_start, TableCtl *ctl)
 {
     __shared__ unsigned s_new;
     if (threadIdx.x == 0) s_new = 0u;
@@ -256,7 +273,10 @@ __global__ void __launch_bounds__(kSortThreads) table_probe_kernel(const u64 *__
         int t = -2;
         if (i == 0 || keys[i - 1] != k) {
             t = table_find(k, slot_keys, slot_idx, log2cap);
-            if (t < 0) mine++;
+            const bool is_long = i + kLongRun - 1 < n && keys[i + kLongRun - 1] == k;      // sorted: the whole stretch is k
+            if (is_long) long_start[atomicAdd(&ctl->n_long, 1u)] = (int32_t)i;
+            if (t < 0) { mine++; t = is_long ? -3 : -1; }
+            else if (is_long) t |= kLongFlag;
         }
         tag[i] = t;
     }
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kSortThreads) table_probe_kernel(const u64 *__
     if (threadIdx.x == 0) tile_new[blockIdx.x] = s_new;
 }
 
-// exclusive scan of tile_new (one CTA), total -> counters[1]; counters[0] = keys in the table before the batch
+// exclusive scan of tile_new (one CTA), total -> counters[1]
 __global__ void __launch_bounds__(kSortThreads) table_scan_kernel(unsigned *__restrict__ tile_new, int64_t tiles,
                                                                   int64_t *__restrict__ counters)
 {
@@ -282,76 +302,114 @@ __global__ void __launch_bounds__(kSortThreads) table_scan_kernel(unsigned *__re
     if (threadIdx.x == 0) counters[1] = (int64_t)carry;
 }
 
-// pass 2: every head walks its run in update order (:56-61, sequential by definition; loads are issued
-// eight at a time ahead of the dependent fp64 chain).  New keys get dense indices in sorted-key order --
-// n_before + new heads in earlier tiles + new heads earlier in this tile -- so the table's layout does not
-// depend on the scheduling of the launch.
-__global__ void __launch_bounds__(kSortThreads) table_apply_kernel(const u64 *__restrict__ keys,
-                                                                   const double *__restrict__ targets, int64_t n, double a,
-                                                                   const int32_t *__restrict__ tag,
-                                                                   const unsigned *__restrict__ tile_base,
-                                                                   u64 *__restrict__ slot_keys, int32_t *__restrict__ slot_idx,
-                                                                   int log2cap, u64 *__restrict__ dense_keys,
-                                                                   double *__restrict__ dense_values, int64_t n_before)
+// thread t looks at records [16 t, 16 t + 16) of the tile: consecutive, so a per-thread count + block scan ranks the new heads
+__global__ void __launch_bounds__(kSortThreads) table_assign_kernel(const u64 *__restrict__ keys, int64_t n,
+                                                                    int32_t *__restrict__ tag,
+                                                                    const unsigned *__restrict__ tile_base,
+                                                                    u64 *__restrict__ slot_keys, int32_t *__restrict__ slot_idx,
+                                                                    int log2cap, u64 *__restrict__ dense_keys,
+                                                                    double *__restrict__ dense_values, int64_t n_before)
 {
     __shared__ unsigned s_warp[kSortWarps];
-    const double keep = __dsub_rn(1.0, a);                                          // (1 - self.a)
     const u64 mask = (1ull << log2cap) - 1ull;
-    const int64_t base = (int64_t)blockIdx.x * kTile;
-    unsigned before = tile_base[blockIdx.x];
-    // thread t owns records [base + 16 t, base + 16 t + 16): consecutive, so a per-thread count + block scan ranks the new heads
+    const int64_t first = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kSortRows;
     int32_t tg[kSortRows];
     unsigned mine = 0;
-    const int64_t first = base + (int64_t)threadIdx.x * kSortRows;
 #pragma unroll
     for (int r = 0; r < kSortRows; r++) {
         tg[r] = first + r < n ? tag[first + r] : -2;
-        mine += tg[r] == -1;
+        mine += tg[r] == -1 || tg[r] == -3;
     }
-    unsigned rank = before + block_scan_256(mine, s_warp, nullptr);
-#pragma unroll 1
+    unsigned rank = tile_base[blockIdx.x] + block_scan_256(mine, s_warp, nullptr);
+    if (!mine) return;
+#pragma unroll
     for (int r = 0; r < kSortRows; r++) {
-        if (tg[r] == -2) continue;
+        if (tg[r] != -1 && tg[r] != -3) continue;
         const int64_t i = first + r;
         const u64 k = keys[i];
-        int64_t di;
-        double v;
-        if (tg[r] >= 0) {
-            di = tg[r];
-            v = dense_values[di];
-        } else {
-            di = n_before + (int64_t)rank++;
-            v = 0.0;                                                                // `if not exists: set(key, 0)` (:52-53)
-            dense_keys[di] = k;
-            for (u64 h = slot_of(k, log2cap);; h = (h + 1) & mask)                  // keys of one batch are distinct: plain CAS claim
-                if (atomicCAS((unsigned long long *)&slot_keys[h], 0ull, (unsigned long long)k) == 0ull) { slot_idx[h] = (int32_t)di; break; }
+        const int64_t di = n_before + (int64_t)rank++;
+        dense_keys[di] = k;
+        dense_values[di] = 0.0;                                                     // `set(key, 0)` (:52-53)
+        for (u64 h = slot_of(k, log2cap);; h = (h + 1) & mask)                      // keys of one batch are distinct: plain CAS claim
+            if (atomicCAS((unsigned long long *)&slot_keys[h], 0ull, (unsigned long long)k) == 0ull) { slot_idx[h] = (int32_t)di; break; }
+        tag[i] = (int32_t)di | (tg[r] == -3 ? kLongFlag : 0);
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) table_apply_kernel(const u64 *__restrict__ keys,
+                                                                   const double *__restrict__ targets, int64_t n, double a,
+                                                                   const int32_t *__restrict__ tag,
+                                                                   const int32_t *__restrict__ long_start, TableCtl *ctl,
+                                                                   double *__restrict__ dense_values)
+{
+    const double keep = __dsub_rn(1.0, a);                                          // (1 - self.a)
+    if (blockIdx.x < kLongBlocks) {
+        // ---- long runs: one warp per run ------------------------------------------------------------
+        const int lane = threadIdx.x & 31;
+        const unsigned n_long = ctl->n_long;
+        for (;;) {
+            unsigned which = 0;
+            if (lane == 0) which = atomicAdd(&ctl->next_long, 1u);
+            which = __shfl_sync(kAll, which, 0);
+            if (which >= n_long) break;
+            const int64_t i = long_start[which];
+            const u64 k = keys[i];
+            const int64_t di = tag[i] & (kLongFlag - 1);
+            // where the run ends: gallop, then bisect, on the sorted keys (every lane the same walk)
+            int64_t lo = i + kLongRun - 1, hi = lo + 1;                             // keys[lo] == k; the end is in (lo, hi]
+            for (int64_t step = kLongRun; hi < n && keys[hi] == k; step <<= 1) { lo = hi; hi = lo + step < n ? lo + step : n; }
+            while (hi - lo > 1) {
+                const int64_t mid = lo + (hi - lo) / 2;
+                if (keys[mid] == k) lo = mid; else hi = mid;
+            }
+            const int64_t end = hi;
+            // The recurrence is sequential by definition; the loads are not.  A window of 32 targets is one
+            // coalesced load (the next window is requested before this one is folded in), the products new * a
+            // are formed by all lanes at once, and every lane then runs the same chain V*(1-a) + p over the window.
+            // The `V == 0` test of the rule (:56) is almost never true after a key's first record, so it is kept
+            // off the dependent chain (DMUL -> DADD per record): a zero met on the way is noticed beside the chain
+            // and the window redone with the test.  Same operations, same roundings, same results.
+            double v = dense_values[di];
+            double x = i + lane < end ? __ldg(targets + i + lane) : 0.0;
+            for (int64_t j = i; j < end; j += 32) {
+                const double nx = j + 32 + lane < end ? __ldg(targets + j + 32 + lane) : 0.0;
+                const double p = __dmul_rn(x, a);
+                if (j + 32 <= end) {
+                    double r = v;
+                    bool zero = false;
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        zero |= r == 0.0;
+                        r = __dadd_rn(__dmul_rn(r, keep), __shfl_sync(kAll, p, q));
+                    }
+                    if (!zero) v = r;
+                    else {
+#pragma unroll 4
+                        for (int q = 0; q < 32; q++) v = smooth_step(v, __shfl_sync(kAll, x, q), keep, a);
+                    }
+                } else {
+                    const int m = (int)(end - j);
+                    for (int q = 0; q < m; q++) v = smooth_step(v, __shfl_sync(kAll, x, q), keep, a);
+                }
+                x = nx;
+            }
+            if (lane == 0) dense_values[di] = v;
         }
-        // where the run ends: gallop, then bisect, on the sorted keys (one load for a run of length one)
-        int64_t lo = i, hi = i + 1;                                                 // keys[lo] == k; the end is in (lo, hi]
-        for (int64_t step = 1; hi < n && keys[hi] == k; step <<= 1) { lo = hi; hi = lo + step < n ? lo + step : n; }
-        if (hi > n) hi = n;
-        while (hi - lo > 1) {
-            const int64_t mid = lo + (hi - lo) / 2;
-            if (keys[mid] == k) lo = mid; else hi = mid;
-        }
-        const int64_t end = hi;                                                     // first record of the next key
-        // the recurrence is sequential by definition (:56-61); the loads are not: a block of 16 targets is
-        // requested while the previous block is being folded in
-        constexpr int kB = 16;
-        double x[kB];
-#pragma unroll
-        for (int q = 0; q < kB; q++) x[q] = i + q < end ? __ldg(targets + i + q) : 0.0;
-        for (int64_t j = i; j < end; j += kB) {
-            double nx[kB];
-#pragma unroll
-            for (int q = 0; q < kB; q++) nx[q] = j + kB + q < end ? __ldg(targets + j + kB + q) : 0.0;
-#pragma unroll
-            for (int q = 0; q < kB; q++)
-                if (j + q < end) v = smooth_step(v, x[q], keep, a);
-#pragma unroll
-            for (int q = 0; q < kB; q++) x[q] = nx[q];
-        }
-        dense_values[di] = v;
+        return;
+    }
+    // ---- short runs: one thread per head ------------------------------------------------------------
+    const int64_t base = (int64_t)(blockIdx.x - kLongBlocks) * kTile;
+#pragma unroll 1
+    for (int r = 0; r < kSortRows; r++) {
+        const int64_t i = base + r * kSortThreads + threadIdx.x;
+        if (i >= n) break;
+        const int32_t tg = tag[i];
+        if (tg < 0 || (tg & kLongFlag)) continue;
+        const u64 k = keys[i];
+        double v = dense_values[tg];
+        int64_t j = i;
+        do { v = smooth_step(v, __ldg(targets + j), keep, a); j++; } while (j < n && keys[j] == k);
+        dense_values[tg] = v;
     }
 }
 
@@ -466,48 +524,65 @@ int othello_partition_records(const uint64_t *keys, const double *values, uint64
     return ob_launch_status();
 }
 
-int64_t othello_table_workspace_bytes(int64_t n)
+// workspace of a probe / apply pair: tag[n] | tile_new[tiles] | long_start[n / kLongRun + 1] | TableCtl
+static size_t ws_align(size_t v) { return (v + 255) & ~(size_t)255; }
+struct TableWs {
+    int32_t *tag; unsigned *tile_new; int32_t *long_start; TableCtl *ctl; size_t bytes;
+};
+static TableWs table_ws(void *workspace, int64_t n)
 {
     const int64_t tiles = n > 0 ? (n + kTile - 1) / kTile : 1;
-    return n * (int64_t)sizeof(int32_t) + tiles * (int64_t)sizeof(unsigned) + 256;
+    char *p = (char *)workspace;
+    TableWs w;
+    size_t off = 0;
+    w.tag = (int32_t *)(p + off); off += ws_align((size_t)n * sizeof(int32_t));
+    w.tile_new = (unsigned *)(p + off); off += ws_align((size_t)tiles * sizeof(unsigned));
+    w.long_start = (int32_t *)(p + off); off += ws_align((size_t)(n / kLongRun + 1) * sizeof(int32_t));
+    w.ctl = (TableCtl *)(p + off); off += 256;
+    w.bytes = off;
+    return w;
 }
+
+int64_t othello_table_workspace_bytes(int64_t n) { return (int64_t)table_ws(nullptr, n < 0 ? 0 : n).bytes; }
 
 int othello_table_probe(const uint64_t *sorted_keys, int64_t n, const uint64_t *slot_keys, const int32_t *slot_idx,
                         int32_t log2_capacity, void *workspace, int64_t workspace_bytes, int64_t *counters, void *stream)
 {
-    OB_CHECK_ARGS(n >= 0 && counters && log2_capacity >= 4 && log2_capacity <= 31);
+    OB_CHECK_ARGS(n >= 0 && n < (1ll << 31) && counters && log2_capacity >= 4 && log2_capacity <= 30);
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) { OB_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(int64_t), s)); return 0; }
     OB_CHECK_ARGS(sorted_keys && slot_keys && slot_idx && workspace && workspace_bytes >= othello_table_workspace_bytes(n));
     const int64_t tiles = (n + kTile - 1) / kTile;
-    int32_t *tag = (int32_t *)workspace;
-    unsigned *tile_new = (unsigned *)((char *)workspace + ((n * sizeof(int32_t) + 255) & ~(size_t)255));
+    const TableWs w = table_ws(workspace, n);
+    OB_CUDA(cudaMemsetAsync(w.ctl, 0, sizeof(TableCtl), s));
     table_probe_kernel<<<(unsigned)tiles, kSortThreads, 0, s>>>((const u64 *)sorted_keys, n, (const u64 *)slot_keys, slot_idx,
-                                                               log2_capacity, tag, tile_new);
-    table_scan_kernel<<<1, kSortThreads, 0, s>>>(tile_new, tiles, counters);
+                                                               log2_capacity, w.tag, w.tile_new, w.long_start, w.ctl);
+    table_scan_kernel<<<1, kSortThreads, 0, s>>>(w.tile_new, tiles, counters);
     return ob_launch_status();
 }
 
 int othello_table_apply(const uint64_t *sorted_keys, const double *sorted_targets, int64_t n, double a,
                         uint64_t *slot_keys, int32_t *slot_idx, int32_t log2_capacity, uint64_t *dense_keys,
-                        double *dense_values, int64_t n_before, const void *workspace, void *stream)
+                        double *dense_values, int64_t n_before, void *workspace, void *stream)
 {
-    OB_CHECK_ARGS(n >= 0 && n_before >= 0 && log2_capacity >= 4 && log2_capacity <= 31);
+    OB_CHECK_ARGS(n >= 0 && n < (1ll << 31) && n_before >= 0 && log2_capacity >= 4 && log2_capacity <= 30);
     if (n == 0) return 0;
     OB_CHECK_ARGS(sorted_keys && sorted_targets && slot_keys && slot_idx && dense_keys && dense_values && workspace);
     const int64_t tiles = (n + kTile - 1) / kTile;
-    const int32_t *tag = (const int32_t *)workspace;
-    const unsigned *tile_base = (const unsigned *)((const char *)workspace + ((n * sizeof(int32_t) + 255) & ~(size_t)255));
-    table_apply_kernel<<<(unsigned)tiles, kSortThreads, 0, (cudaStream_t)stream>>>(
-        (const u64 *)sorted_keys, sorted_targets, n, a, tag, tile_base, (u64 *)slot_keys, slot_idx, log2_capacity,
-        (u64 *)dense_keys, dense_values, n_before);
+    const TableWs w = table_ws(workspace, n);
+    cudaStream_t s = (cudaStream_t)stream;
+    table_assign_kernel<<<(unsigned)tiles, kSortThreads, 0, s>>>((const u64 *)sorted_keys, n, w.tag, w.tile_new,
+                                                                (u64 *)slot_keys, slot_idx, log2_capacity, (u64 *)dense_keys,
+                                                                dense_values, n_before);
+    table_apply_kernel<<<(unsigned)(tiles + kLongBlocks), kSortThreads, 0, s>>>((const u64 *)sorted_keys, sorted_targets, n, a,
+                                                                                w.tag, w.long_start, w.ctl, dense_values);
     return ob_launch_status();
 }
 
 int othello_table_rehash(const uint64_t *dense_keys, int64_t n, uint64_t *slot_keys, int32_t *slot_idx,
                          int32_t log2_capacity, void *stream)
 {
-    OB_CHECK_ARGS(n >= 0 && log2_capacity >= 4 && log2_capacity <= 31 && n <= (1ll << log2_capacity) / 2);
+    OB_CHECK_ARGS(n >= 0 && log2_capacity >= 4 && log2_capacity <= 30 && n <= (1ll << log2_capacity) / 2);
     if (n == 0) return 0;
     OB_CHECK_ARGS(dense_keys && slot_keys && slot_idx);
     table_rehash_kernel<<<ob_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64 *)dense_keys, n, (u64 *)slot_keys,
