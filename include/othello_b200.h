@@ -151,8 +151,8 @@ int othello_playout(const othello_playout_args *args, void *stream);
  * othello_perft: synchronous, result is a HOST pointer; OTHELLO_E_WORKSPACE if a frontier did not fit.
  * othello_perft_async: only enqueues; result is a DEVICE uint64[2] = {nodes, 1 if the workspace was too
  * small}, valid in stream order.  part / nparts split the depth-first stage: the call counts the frontier
- * nodes i = part (mod nparts) (and, for part 0, the game-over leaves met while expanding), so the sum of
- * the nparts results is the node count -- one u64 all-reduce across GPUs. */
+ * nodes whose position hashes to `part` (and, for part 0, the game-over leaves met while expanding), so the
+ * sum of the nparts results is the node count -- one u64 all-reduce across GPUs. */
 int64_t othello_perft_workspace_bytes(int depth);
 int othello_perft(uint64_t black, uint64_t white, int turn, int depth, void *workspace, int64_t workspace_bytes,
                   uint64_t *result, void *stream);

@@ -19,6 +19,20 @@ __device__ constexpr u64 kClassMask[8] = {
     0x8100000000000081ull, 0x4281000000008142ull, 0x0042000000004200ull, 0x2400810000810024ull,
     0x1800008181000018ull, 0x003C424242423C00ull, 0x0000240000240000ull, 0x0000183C3C180000ull};
 
+// Board.mask_count(side, class k) (board.py:74-81) for the eight classes.  Every class mask is mirror
+// symmetric and its low and high words occupy different bit positions, so the two halves of the board can
+// be merged before counting: one POPC instead of two and no add.
+__device__ __forceinline__ int class_count(u64 bb, int k)
+{
+    const u32 mlo = (u32)kClassMask[k], mhi = (u32)(kClassMask[k] >> 32);
+    return __popc(((u32)bb & mlo) | ((u32)(bb >> 32) & mhi));
+}
+static_assert(((kClassMask[0] >> 32) & kClassMask[0] & 0xffffffffull) == 0 && ((kClassMask[1] >> 32) & kClassMask[1] & 0xffffffffull) == 0 &&
+              ((kClassMask[2] >> 32) & kClassMask[2] & 0xffffffffull) == 0 && ((kClassMask[3] >> 32) & kClassMask[3] & 0xffffffffull) == 0 &&
+              ((kClassMask[4] >> 32) & kClassMask[4] & 0xffffffffull) == 0 && ((kClassMask[5] >> 32) & kClassMask[5] & 0xffffffffull) == 0 &&
+              ((kClassMask[6] >> 32) & kClassMask[6] & 0xffffffffull) == 0 && ((kClassMask[7] >> 32) & kClassMask[7] & 0xffffffffull) == 0,
+              "class masks: low and high words must not share bit positions");
+
 // ---- counter-based RNG (DESIGN.md "RNG"; oracle restatement: orc_rng_*) ----------------------
 __device__ __forceinline__ u32 fmix32(u32 h)
 {
@@ -65,7 +79,7 @@ __device__ __forceinline__ void features10(u64 own, u64 opp, int f[10])
     f[0] = __popcll(own | opp);
     f[1] = __popcll(obf::legal_moves(own, opp));
 #pragma unroll
-    for (int k = 0; k < 8; k++) f[2 + k] = __popcll(own & kClassMask[k]);
+    for (int k = 0; k < 8; k++) f[2 + k] = class_count(own, k);
 }
 
 // w[phase] . (mobility, a..h) + w[phase][9]; w = [4][10] floats (shared or global)
@@ -76,7 +90,7 @@ __device__ __forceinline__ float eval_linear(u64 own, u64 opp, const float *__re
     float acc = row[9];
     acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)__popcll(own & kClassMask[k]), acc);
+    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)class_count(own, k), acc);
     return acc;
 }
 

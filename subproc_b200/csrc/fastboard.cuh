@@ -152,35 +152,60 @@ OBF_HD Inter moves_up(Inter own, Inter opp, Inter m)
     return r;
 }
 
-// Board.puttables(piece) as a mask (board.py:46-52).
-OBF_HD u64 legal_moves(u64 own, u64 opp)
+// A position prepared for move generation: both colours in the row-interleaved layout, as they stand
+// and rotated by 180 degrees.  Swapping the roles of the colours is free (swap the members), and a
+// successor position is two ORs / AND-NOTs away (see child_mobility).
+struct Pos4 { Inter o, p, ro, rp; };
+
+OBF_HD Pos4 make_pos4(u64 own, u64 opp)
 {
     const Inter o = to_inter(own), p = to_inter(opp);
-    const Inter m = Inter{p.a & kInner32, p.b & kInner32};
-    const Inter up = moves_up(o, p, m);
-    const Inter down = moves_up(rev_inter(o), rev_inter(p), rev_inter(m));   // the rotated board
-    return from_inter(ior(up, rev_inter(down))) & ~(own | opp);
+    return Pos4{o, p, rev_inter(o), rev_inter(p)};
 }
+OBF_HD Pos4 swapped(const Pos4 &q) { return Pos4{q.p, q.o, q.rp, q.ro}; }
+
+// legal moves of colour `o`, still in the interleaved layout (popcount it, or from_inter() it)
+OBF_HD Inter legal_inter(const Pos4 &q)
+{
+    // kInner32 is a palindrome, so the rotated inner mask is the same constant
+    const Inter m = Inter{q.p.a & kInner32, q.p.b & kInner32}, mr = Inter{q.rp.a & kInner32, q.rp.b & kInner32};
+    const Inter up = moves_up(q.o, q.p, m);
+    const Inter down = moves_up(q.ro, q.rp, mr);                              // the rotated board
+    return iand(ior(up, rev_inter(down)), Inter{~(q.o.a | q.p.a), ~(q.o.b | q.p.b)});
+}
+
+OBF_HD int popc_inter(Inter v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v.a) + __popc(v.b);
+#else
+    return __builtin_popcount(v.a) + __builtin_popcount(v.b);
+#endif
+}
+
+// Board.puttables(piece) as a mask (board.py:46-52).
+OBF_HD u64 legal_moves(u64 own, u64 opp) { return from_inter(legal_inter(make_pos4(own, opp))); }
+
+// n_puttable_for(mover) AFTER the mover has played: `placed` = the new disc + the discs it flipped.  The
+// successor is built from the prepared parent (own' = own | placed, opp' = opp & ~placed), so a child costs one
+// layout conversion and one rotation of `placed` instead of two of each for two full boards, and nothing is
+// converted back (a popcount does not care about the layout).
+OBF_HD int child_mobility(const Pos4 &parent, u64 placed)
+{
+    const Inter d = to_inter(placed), rd = rev_inter(d);
+    const Pos4 c = Pos4{ior(parent.o, d), Inter{parent.p.a & ~d.a, parent.p.b & ~d.b},
+                        ior(parent.ro, rd), Inter{parent.rp.a & ~rd.a, parent.rp.b & ~rd.b}};
+    return popc_inter(legal_inter(c));
+}
+
 // n_puttable_for() of BOTH colours of one position (the mobility feature of counts(),
 // parameter_progress_position_moves_learn.py:8): the layout conversions and rotations of the two
 // boards are shared, and a popcount does not care about the layout, so nothing is converted back.
 OBF_HD void mobility_both(u64 black, u64 white, int &mob_black, int &mob_white)
 {
-    const Inter b = to_inter(black), w = to_inter(white);
-    const Inter mb = Inter{b.a & kInner32, b.b & kInner32}, mw = Inter{w.a & kInner32, w.b & kInner32};
-    const Inter br = rev_inter(b), wr = rev_inter(w);
-    // kInner32 is a palindrome, so the rotated inner mask is the same constant
-    const Inter mbr = Inter{br.a & kInner32, br.b & kInner32}, mwr = Inter{wr.a & kInner32, wr.b & kInner32};
-    const Inter empty = Inter{~(b.a | w.a), ~(b.b | w.b)};
-    const Inter lb = iand(ior(moves_up(b, w, mw), rev_inter(moves_up(br, wr, mwr))), empty);
-    const Inter lw = iand(ior(moves_up(w, b, mb), rev_inter(moves_up(wr, br, mbr))), empty);
-#if defined(__CUDA_ARCH__)
-    mob_black = __popc(lb.a) + __popc(lb.b);
-    mob_white = __popc(lw.a) + __popc(lw.b);
-#else
-    mob_black = __builtin_popcount(lb.a) + __builtin_popcount(lb.b);
-    mob_white = __builtin_popcount(lw.a) + __builtin_popcount(lw.b);
-#endif
+    const Pos4 q = make_pos4(black, white);
+    mob_black = popc_inter(legal_inter(q));
+    mob_white = popc_inter(legal_inter(swapped(q)));
 }
 
 // (own_r / opp_r = rev64(own / opp) are what flips_for needs; move generation rotates in its own layout)

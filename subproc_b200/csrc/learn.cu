@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(kThreads, 3) learn_kernel(const u64 *__restric
                 obf::mobility_both(b, w, x[0][0], x[1][0]);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    x[0][1 + k] = __popcll(b & kClassMask[k]);
-                    x[1][1 + k] = __popcll(w & kClassMask[k]);
+                    x[0][1 + k] = class_count(b, k);
+                    x[1][1 + k] = class_count(w, k);
                 }
             }
             // a lane's shard changes at most once inside a block (8 plies < 16 discs): close its partial sums;

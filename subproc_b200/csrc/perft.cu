@@ -14,7 +14,7 @@
 // is not needed (frontier already large enough, or one ply left) returns at once; the last CTA of a
 // step that did expand publishes the new frontier.  No host round trip per level, so the sequence is
 // stream-ordered, capturable in a CUDA graph, and its result can stay on the device (multi-GPU: every
-// rank counts the frontier nodes i = part (mod nparts) and the ranks add their counts).
+// rank counts the frontier nodes whose position hashes to its part and the ranks add their counts).
 #include "common.cuh"
 
 using namespace ob;
@@ -146,23 +146,31 @@ template <> struct Dfs<1> {
     }
 };
 
-// count the subtrees of the frontier nodes i = part (mod nparts); warps fetch 32 nodes at a time
+// which of the nparts shares counts the subtree of a frontier node: a function of the POSITION, because the
+// order in which a breadth-first expansion appends nodes differs from run to run and from GPU to GPU
+__device__ __forceinline__ unsigned part_of(u64 own, u64 opp, unsigned nparts)
+{
+    u64 h = own * 0x9E3779B97F4A7C15ull ^ opp * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    return (unsigned)(((h & 0xffffffffull) * nparts) >> 32);
+}
+
+// count the subtrees of this part's frontier nodes; warps fetch 32 nodes at a time
 template <int R>
 __device__ __forceinline__ void dfs_all(const u64 *own, const u64 *opp, unsigned long long n, unsigned part,
                                         unsigned nparts, Ctl *ctl, const Rays &rays)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned long long mine = n > part ? (n - part + nparts - 1) / nparts : 0;   // nodes of this part
     unsigned long long c = 0;
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctl->next, 32ull);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= mine) break;
-        const unsigned long long j = base + lane;
-        if (j < mine) {
-            const unsigned long long i = j * nparts + part;
-            c += Dfs<R>::run(own[i], opp[i], rays);
+        if (base >= n) break;
+        const unsigned long long i = base + lane;
+        if (i < n) {
+            const u64 o = own[i], p = opp[i];
+            if (nparts == 1 || part_of(o, p, nparts) == part) c += Dfs<R>::run(o, p, rays);
         }
     }
     c = warp_sum(c);

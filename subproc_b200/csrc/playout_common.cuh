@@ -21,7 +21,7 @@ __device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__rest
     float acc = row[9];
     acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)__popcll(own & ob::kClassMask[k]), acc);
+    for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)ob::class_count(own, k), acc);
     return acc;
 }
 

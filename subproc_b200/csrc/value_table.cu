@@ -28,14 +28,14 @@ __device__ __forceinline__ u64 pack_features(u64 side, u64 other)
 {
     u64 k = (u64)__popcll(side | other);
     k = (k << 6) | (u64)__popcll(obf::legal_moves(side, other));
-    k = (k << 3) | (u64)__popcll(side & kClassMask[0]);
-    k = (k << 4) | (u64)__popcll(side & kClassMask[1]);
-    k = (k << 3) | (u64)__popcll(side & kClassMask[2]);
-    k = (k << 4) | (u64)__popcll(side & kClassMask[3]);
-    k = (k << 4) | (u64)__popcll(side & kClassMask[4]);
-    k = (k << 5) | (u64)__popcll(side & kClassMask[5]);
-    k = (k << 3) | (u64)__popcll(side & kClassMask[6]);
-    k = (k << 4) | (u64)__popcll(side & kClassMask[7]);
+    k = (k << 3) | (u64)class_count(side, 0);
+    k = (k << 4) | (u64)class_count(side, 1);
+    k = (k << 3) | (u64)class_count(side, 2);
+    k = (k << 4) | (u64)class_count(side, 3);
+    k = (k << 4) | (u64)class_count(side, 4);
+    k = (k << 5) | (u64)class_count(side, 5);
+    k = (k << 3) | (u64)class_count(side, 6);
+    k = (k << 4) | (u64)class_count(side, 7);
     return k;
 }
 

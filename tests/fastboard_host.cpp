@@ -33,3 +33,15 @@ extern "C" void fb_mobility_both(const unsigned long long *black, const unsigned
 {
     for (long i = 0; i < n; i++) obf::mobility_both(black[i], white[i], mb[i], mw[i]);
 }
+
+extern "C" void fb_child_mobility(const unsigned long long *own, const unsigned long long *opp, const unsigned char *sq,
+                                  int *out, long n)
+{
+    init();
+    for (long i = 0; i < n; i++) {
+        const unsigned long long x = 1ull << sq[i];
+        const unsigned long long f = ((own[i] | opp[i]) & x) ? 0ull
+                 : obf::flips_for(sq[i], own[i], opp[i], obf::rev64(own[i]), obf::rev64(opp[i]), Rays());
+        out[i] = f ? obf::child_mobility(obf::make_pos4(own[i], opp[i]), f | x) : -1;
+    }
+}

@@ -87,3 +87,24 @@ def test_mobility_of_both_colours_in_one_pass(fb, oracle):
     fb.fb_mobility_both(P(b), P(w), P(mb), P(mw), ctypes.c_long(n))
     pop = lambda a: np.array([bin(int(v)).count("1") for v in a], dtype=np.int32)
     assert np.array_equal(mb, pop(oracle.puttables(b, w, 1))) and np.array_equal(mw, pop(oracle.puttables(b, w, 2)))
+
+
+def test_child_mobility_from_the_prepared_parent(fb, oracle):
+    """obf::child_mobility (successor built in the interleaved layout from the parent + the placed discs) ==
+    the mover's n_puttable_for after put() in the oracle"""
+    b, w = positions(oracle, 200, 53)
+    n = b.size
+    rng = np.random.RandomState(4)
+    for own, opp, piece in ((b, w, 1), (w, b, 2)):
+        legal = oracle.puttables(b, w, piece)
+        sq = rng.randint(0, 64, size=n).astype(np.uint8)
+        for i in range(n):
+            if legal[i]:
+                bits = [s for s in range(64) if (int(legal[i]) >> s) & 1]
+                sq[i] = bits[rng.randint(len(bits))]
+        got = np.zeros(n, np.int32)
+        fb.fb_child_mobility(P(own), P(opp), P(sq), P(got), ctypes.c_long(n))
+        nb, nw, flips, _ = oracle.put(b, w, piece, sq)
+        after = oracle.puttables(nb, nw, piece)
+        want = np.array([bin(int(v)).count("1") if f else -1 for v, f in zip(after, flips)], dtype=np.int32)
+        assert np.array_equal(got, want)

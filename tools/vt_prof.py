@@ -48,10 +48,14 @@ for label in ("first_update", "second_update", "third_update"):      # second: e
 # whole update incl. the records kernel, wall clock
 vt2 = value_table.ValueTable(device=dev)
 vt2.update_from_playout(po)
-torch.cuda.synchronize(); t0 = time.perf_counter()
-vt2.update_from_playout(po)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+dts = []
+for _ in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    vt2.update_from_playout(po)
+    torch.cuda.synchronize()
+    dts.append(time.perf_counter() - t0)
+out["update_from_playout_all_ms"] = [round(1e3 * d, 3) for d in dts]
+dt = min(dts)
 out["update_from_playout_ms"] = 1e3 * dt
 out["records_per_s"] = n / dt
 out["table_keys"] = len(vt2)
