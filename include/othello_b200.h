@@ -190,6 +190,12 @@ int othello_learn_stats(const int64_t *acc, double *stats, void *stream);
 int othello_learn_solve(const double *stats, const float *prev_weights, float *weights, int32_t *params,
                         double *fits, void *stream);
 
+/* One learning step's refit in ONE launch, straight from the (all-reduced) accumulators: othello_learn_stats +
+ * othello_learn_solve, the statistics passing through shared memory (also written to `stats` if not NULL).
+ * clear != 0 leaves acc zeroed for the next iteration's othello_learn_accumulate.  DEVICE pointers. */
+int othello_learn_refit(int64_t *acc, int32_t clear, double *stats /* [4][112] or NULL */, const float *prev_weights,
+                        float *weights, int32_t *params, double *fits, void *stream);
+
 /* ---- the reference's value table, exactly ------------------------------------------------------ */
 
 /* __update_state_for_a_book (progress_position_moves_learn.py:37-48): one (key, new_value) record per

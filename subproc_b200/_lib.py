@@ -66,6 +66,7 @@ SIGNATURES = {
                                            ctypes.c_int, vp, i64, vp, vp]),
     "othello_learn_accumulate": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp]),
     "othello_learn_stats": (ctypes.c_int, [vp, vp, vp]),
+    "othello_learn_refit": (ctypes.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "othello_learn_solve": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "othello_value_records": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
     "othello_sort_workspace_bytes": (i64, [i64]),

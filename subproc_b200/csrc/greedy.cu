@@ -46,10 +46,10 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     __shared__ float w_s[2 * kW];                             // Black's table, then White's
     __shared__ u64 ray_s[obf::kRayDirs * 64];
     __shared__ WarpScratch scratch[kWarps];
-    if (threadIdx.x < 2 * kW) {
-        const float *src = threadIdx.x < kW ? (a.weights ? a.weights : a.weights_white)
-                                            : (a.weights_white ? a.weights_white : a.weights);
-        w_s[threadIdx.x] = src[threadIdx.x % kW];
+    for (int i = threadIdx.x; i < 2 * kW; i += blockDim.x) {    // (a CTA is 2 or 4 warps, see ob_launch_greedy)
+        const float *src = i < kW ? (a.weights ? a.weights : a.weights_white)
+                                  : (a.weights_white ? a.weights_white : a.weights);
+        w_s[i] = src[i % kW];
     }
     // which colours are served by the greedy engine (the other answers uniformly at random)
     const bool greedy_b = a.policy == OTHELLO_POLICY_GREEDY;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     // a warp plays `gpw` games (one per lane, lanes >= gpw only help evaluating children): 32 for large
     // batches; fewer for small ones, so that a batch of 2^16 games still fills every SM with warps
     const int gpw = a.games_per_warp;
-    const int64_t g = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * gpw + lane;
+    const int64_t g = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * gpw + lane;
     bool done = lane >= gpw || g >= a.n_games;                // lanes without a game only help evaluating
     const int64_t gi = done ? 0 : g;
     const u64 b0 = a.black0 ? a.black0[gi] : OTHELLO_START_BLACK;
@@ -187,14 +187,17 @@ int ob_launch_greedy(const othello_playout_args &args, cudaStream_t s)
     if (a.games_per_warp != 8 && a.games_per_warp != 16 && a.games_per_warp != 32) {
         a.games_per_warp = 32;
     }
-    const unsigned blocks = ob_blocks(a.n_games, a.games_per_warp * kWarps);
+    // Small batches (less than two waves of 6 CTAs x 148 SMs) run as CTAs of 2 warps instead of 4: twice as
+    // many CTAs spread evenly over the SMs (2^16 games: 6.9 per SM instead of 3.5, i.e. 7 vs 4 on the fullest)
+    const int threads = a.n_games < 2 * 6 * 148 * kThreads ? kThreads / 2 : kThreads;
+    const unsigned blocks = ob_blocks(a.n_games, a.games_per_warp * (threads / 32));
     const bool subst = a.n_rand_black > 0 || a.n_rand_white > 0;
     if (a.traj_black) {
-        if (subst) greedy_kernel<true, true><<<blocks, kThreads, 0, s>>>(a);
-        else greedy_kernel<false, true><<<blocks, kThreads, 0, s>>>(a);
+        if (subst) greedy_kernel<true, true><<<blocks, threads, 0, s>>>(a);
+        else greedy_kernel<false, true><<<blocks, threads, 0, s>>>(a);
     } else {
-        if (subst) greedy_kernel<true, false><<<blocks, kThreads, 0, s>>>(a);
-        else greedy_kernel<false, false><<<blocks, kThreads, 0, s>>>(a);
+        if (subst) greedy_kernel<true, false><<<blocks, threads, 0, s>>>(a);
+        else greedy_kernel<false, false><<<blocks, threads, 0, s>>>(a);
     }
     return ob_launch_status();
 }

@@ -26,8 +26,10 @@
 // The blocks are fixed multiples of 8 plies, so the fp64 partial sums do not depend on the launch geometry.
 #include "common.cuh"
 #include "fastboard.cuh"
+#include "learn_acc.cuh"
 
 using namespace ob;
+using namespace obl;
 
 namespace {
 
@@ -35,15 +37,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = 32 * kWarps;
 constexpr int kPlyBlock = 8;                 // plies per unit of work (fixed: part of the definition of the fp64 sums)
 constexpr int kGames = 32;                   // games per CTA (one per lane)
-constexpr int kX = 10;                       // regressors incl. intercept
-constexpr int kFp = 10;                      // fp64 sums per shard: Xty[0..8] (Xty[9] is identically 0), sum y^2
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kPairs = kX * (kX + 1) / 2;    // upper triangle of XtX
-constexpr int kFpBase = 56;                  // acc[shard][kFpBase + 2 k], [.. + 1] = high, low word of fp sum k
-constexpr double kFixScale = 1099511627776.0;            // 2^40
-static_assert(kFpBase >= kPairs && kFpBase + 2 * kFp <= OTHELLO_ACC, "accumulator layout");
-
-__host__ __device__ constexpr int pair_index(int i, int j) { return i * kX - i * (i - 1) / 2 + (j - i); }
 
 // D[16x8] += A[16x32] * B[32x8], signed 8-bit operands, 32-bit accumulators (tensor cores)
 __device__ __forceinline__ void mma_s8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
@@ -256,24 +250,7 @@ __global__ void __launch_bounds__(128) stats_kernel(const long long *__restrict_
     const int s = blockIdx.x;
     const long long *a = acc + s * OTHELLO_ACC;
     double *out = stats + s * OTHELLO_STATS;
-    for (int k = threadIdx.x; k < OTHELLO_STATS; k += blockDim.x) {
-        double v;
-        if (k < kX * kX) {
-            const int i = k / kX, j = k % kX;
-            v = (double)a[i <= j ? pair_index(i, j) : pair_index(j, i)];
-        } else if (k == 110) {
-            v = (double)a[pair_index(kX - 1, kX - 1)];        // n = sum of intercept * intercept
-        } else {
-            const int q = k == 111 ? kFp - 1 : k - kX * kX;    // sum y^2 | Xty[q]
-            if (q == kX - 1 && k != 111) { out[k] = 0.0; continue; }                 // Xty[intercept] cancels exactly
-            long long hi = a[kFpBase + 2 * q];
-            unsigned long long lo = (unsigned long long)a[kFpBase + 2 * q + 1];
-            hi += (long long)(lo >> 32);                       // normalise: exact integer arithmetic
-            lo &= 0xffffffffull;
-            v = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / kFixScale);        // one rounding
-        }
-        out[k] = v;
-    }
+    for (int k = threadIdx.x; k < OTHELLO_STATS; k += blockDim.x) out[k] = stat_from_acc(a, k);
 }
 
 }  // namespace

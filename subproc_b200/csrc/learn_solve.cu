@@ -9,6 +9,7 @@
 // toward zero (:200).  One warp per shard; the symmetric eigen-decomposition is parallel-order cyclic
 // Jacobi in fp64 (9x9: 9 rounds of 4 disjoint rotations per sweep, a handful of sweeps).
 #include "common.cuh"
+#include "learn_acc.cuh"
 
 namespace {
 
@@ -17,14 +18,11 @@ constexpr int kSweeps = 16;
 
 // (prev_weights and weights may be the same table -- a shard without samples copies its own row -- so
 // neither carries __restrict__)
-__global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ stats, const float *prev_weights,
-                                                   float *weights, int32_t *__restrict__ params,
-                                                   double *__restrict__ fits, double rcond)
+__device__ __forceinline__ void solve_shard(const double *row, int s, int lane, const float *prev_weights, float *weights,
+                                            int32_t *__restrict__ params, double *__restrict__ fits, double rcond)
 {
     __shared__ double A[kN][kN], V[kN][kN], sxy[kN], coef[kN], xbar[kN], lam_inv[kN];
     __shared__ int live[kN];
-    const int s = blockIdx.x, lane = threadIdx.x;
-    const double *row = stats + (size_t)s * OTHELLO_STATS;
     const double *xtx = row, *xty = row + 100;
     const double n = row[110], syy = row[111];
     float *w_out = weights + s * OTHELLO_WEIGHTS;
@@ -151,7 +149,42 @@ __global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ st
     }
 }
 
+__global__ void __launch_bounds__(32) solve_kernel(const double *__restrict__ stats, const float *prev_weights,
+                                                   float *weights, int32_t *__restrict__ params,
+                                                   double *__restrict__ fits, double rcond)
+{
+    solve_shard(stats + (size_t)blockIdx.x * OTHELLO_STATS, blockIdx.x, threadIdx.x, prev_weights, weights, params, fits, rcond);
+}
+
+// the same from the exact integer accumulators, in one launch: accumulators -> statistics (shared memory, and
+// `stats` if wanted) -> regression; `clear` leaves the accumulators zeroed for the next iteration
+__global__ void __launch_bounds__(32) refit_kernel(long long *__restrict__ acc, int clear, double *__restrict__ stats,
+                                                   const float *prev_weights, float *weights, int32_t *__restrict__ params,
+                                                   double *__restrict__ fits, double rcond)
+{
+    __shared__ double row[OTHELLO_STATS];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    long long *a = acc + s * OTHELLO_ACC;
+    for (int k = lane; k < OTHELLO_STATS; k += 32) {
+        row[k] = obl::stat_from_acc(a, k);
+        if (stats) stats[s * OTHELLO_STATS + k] = row[k];
+    }
+    __syncwarp();
+    if (clear)
+        for (int k = lane; k < OTHELLO_ACC; k += 32) a[k] = 0;
+    solve_shard(row, s, lane, prev_weights, weights, params, fits, rcond);
+}
+
 }  // namespace
+
+extern "C" int othello_learn_refit(int64_t *acc, int32_t clear, double *stats, const float *prev_weights, float *weights,
+                                   int32_t *params, double *fits, void *stream)
+{
+    OB_CHECK_ARGS(acc && prev_weights && weights && params && fits);
+    refit_kernel<<<OTHELLO_PHASES, 32, 0, (cudaStream_t)stream>>>((long long *)acc, clear, stats, prev_weights, weights, params,
+                                                                 fits, 1e-12);
+    return ob_launch_status();
+}
 
 extern "C" int othello_learn_solve(const double *stats, const float *prev_weights, float *weights, int32_t *params,
                                    double *fits, void *stream)

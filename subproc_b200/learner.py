@@ -240,7 +240,7 @@ class ProgressPositionMovesLearn(object):
     def self_play_iterations_on_device(self, n_iterations, games_per_rank, seed=0, first_iteration=0, random_plies=10,
                                        device=None, rank=0, world=1, t_max=120):
         """config 5 without host round trips: every iteration is playout -> statistics -> all-reduce ->
-        othello_learn_solve -> the next playout reads the new table straight from device memory.  The
+        othello_learn_refit -> the next playout reads the new table straight from device memory.  The
         host only enqueues; parameters are copied back once at the end.  Same arithmetic as
         ``self_play_iteration`` on identical statistics (the integer parameters may differ by one where a
         scaled coefficient sits on an integer boundary: two eigen-solvers, last-ulp differences)."""
@@ -255,11 +255,10 @@ class ProgressPositionMovesLearn(object):
             gid0 = (it * world + rank) * games_per_rank
             po = ops.playout(games_per_rank, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
                              random_plies=random_plies, weights=w, t_max=t_max, out=po)
-            acc.zero_()
             ops.learn_accumulate(po, acc=acc, lam=self.l)
             allreduce_stats(acc)
-            ops.learn_stats(acc, out=stats)
-            w, params, fits = ops.learn_solve(stats, w, weights_out=w)     # in place: the solver allows the alias
+            # statistics + four regressions + clearing the accumulators: one launch, weights updated in place
+            w, params, fits = ops.learn_refit(acc, w, weights_out=w, clear=True, stats_out=stats, params=params, fits=fits)
         self.params = [int(v) for v in params.cpu().tolist()]
         f = fits.cpu().numpy()
         self.last_fits = [dict(coef=f[s, :9].copy(), intercept=float(f[s, 9]), rmse=float(f[s, 10]), r2=float(f[s, 11]),

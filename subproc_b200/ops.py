@@ -368,6 +368,22 @@ def learn_solve(stats, prev_weights, weights_out=None):
     return weights_out, params, fits
 
 
+def learn_refit(acc, prev_weights, weights_out=None, clear=True, stats_out=None, params=None, fits=None):
+    """accumulators int64 [4][80] -> (weights, params, fits) in one launch (othello_learn_refit); ``clear`` zeroes
+    the accumulators for the next iteration, ``stats_out`` (float64 [4][112]) also receives the statistics."""
+    dev = acc.device
+    weights_out = torch.empty((4, 10), dtype=torch.float32, device=dev) if weights_out is None else weights_out
+    params = torch.empty(36, dtype=torch.int32, device=dev) if params is None else params
+    fits = torch.empty((4, 16), dtype=torch.float64, device=dev) if fits is None else fits
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().othello_learn_refit(
+            _req(acc, torch.int64, 4 * N_ACC, "acc"), 1 if clear else 0, _opt(stats_out, torch.float64, 448, "stats_out"),
+            _req(prev_weights, torch.float32, 40, "prev_weights"), _req(weights_out, torch.float32, 40, "weights_out"),
+            _req(params, torch.int32, 36, "params"), _req(fits, torch.float64, 64, "fits"), _stream(acc)),
+            "othello_learn_refit")
+    return weights_out, params, fits
+
+
 def int32_peak(device=None, iters=4096, blocks_per_sm=8, threads=256, repeats=5, dual=False):
     """Measured INT32 throughput (lane-ops/s) of this GPU: the integer roofline denominator.
 

@@ -95,3 +95,20 @@ def test_iterations_on_device_track_the_host_loop():
     assert [f['n'] for f in A.last_fits] == [f['n'] for f in B.last_fits]
     B.self_play_iterations_on_device(3, 8192, seed=5, first_iteration=1, device=DEV)
     assert all(-127 <= v <= 127 for v in B.read_parameters()[1:]) and B.last_processed() == 4 * 8192 - 1
+
+
+def test_refit_in_one_launch_equals_stats_then_solve():
+    """othello_learn_refit == othello_learn_stats + othello_learn_solve, bit for bit, and clears the accumulators"""
+    from subproc_b200 import parameter
+    w0 = torch.from_numpy(parameter.ProgressPositionMovesParameter().weights_table()).to(DEV)
+    po = ops.playout(6000, seed=15, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, random_plies=8, weights=w0)
+    acc = ops.learn_accumulate(po)
+    stats = ops.learn_stats(acc)
+    w_a, p_a, f_a = ops.learn_solve(stats, w0)
+    stats_b = torch.zeros_like(stats)
+    w_b, p_b, f_b = ops.learn_refit(acc.clone(), w0, clear=False, stats_out=stats_b)
+    assert torch.equal(stats, stats_b) and torch.equal(w_a, w_b) and torch.equal(p_a, p_b) and torch.equal(f_a, f_b)
+    acc2 = acc.clone()
+    w_c = w0.clone()
+    ops.learn_refit(acc2, w_c, weights_out=w_c, clear=True)              # in place on the weight table
+    assert int(acc2.abs().sum()) == 0 and torch.equal(w_c, w_a)
