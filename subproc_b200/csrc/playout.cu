@@ -69,19 +69,10 @@ template <bool TRAJ, bool UNIFORM>
 // (128 threads x >= 10 CTAs per SM measured best on B200: 64/128/256 threads and 9..12 CTAs are within 2 %)
 __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
 {
-#if defined(OB_WARP_RAYS)
-    // every warp keeps its own copy of the 2 KB ray table: no CTA-wide barrier before the first ply
-    __shared__ u64 ray_s[kThreads / 32][obf::kRayDirs * 64];
-    u64 *my_rays = ray_s[threadIdx.x >> 5];
-    for (int i = threadIdx.x & 31; i < obf::kRayDirs * 64; i += 32) my_rays[i] = kRayTable.v[i];
-    __syncwarp();
-    const Rays rays = {my_rays};
-#else
     __shared__ u64 ray_s[obf::kRayDirs * 64];
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
-#endif
     const int64_t gi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool live = gi < a.n_games;                  // lanes past the batch only take part in the totals
     int plies = 0, n_black = 0, n_white = 0;
