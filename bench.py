@@ -521,23 +521,26 @@ def run_b200_arm(args):
                          "50 B of HBM traffic per position" % t_open}
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------
-    # The call a user without torch makes: start positions in pinned host memory go
-    # in, per-game results (plies, final position) and the batch totals come back to pinned host
-    # memory, every step.  Two batches are kept in flight (othello_playout_host_async / othello_ctx_wait),
-    # so the PCIe copies of one step run under the kernels of its neighbours; the timed region still
-    # starts with nothing in flight and ends when the last result of step K is in host memory.
+    # The call a user without torch makes: start positions in pinned host memory go in
+    # (16 B per game), the per-game results come back to pinned host memory as two-byte summaries (plies,
+    # disc difference: what store_batch_stats reads of a game, learn_base.py:70-98) together with the batch
+    # totals, every step.  Two batches are kept in flight (othello_playout_host_async / othello_ctx_wait), so
+    # the PCIe copies of one step run under the kernels of its neighbours; the timed region still starts with
+    # nothing in flight and ends when the last result of step K is in host memory.  (The full 20 B per game --
+    # plies as int32 + the final position -- is measured next to it: on an 8-GPU host the PCIe fabric, not the
+    # GPUs, then sets the pace, see profiles/e2e_breakdown_r02_*.json.)
     L = _lib.lib()
     ctx = ctypes.c_void_p()
     _lib.check(L.othello_ctx_create(local, ctypes.byref(ctx)), "othello_ctx_create")
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
     h_b0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_BLACK))
     h_w0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_WHITE))
-    h_t0 = pin(G, torch.uint8).fill_(ops.BLACK)
-    h_out = [(pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64), pin(4, torch.int64)) for _ in range(2)]
+    h_out = [(pin(G, torch.int16), pin(4, torch.int64), pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64))
+             for _ in range(2)]
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     e2e_gid = [gid_base + (W + K + 3) * G]
 
-    def e2e_run(steps):
+    def e2e_run(steps, full=False):
         """issue step i+1, then collect step i; returns the positions played (from the batch totals)"""
         tickets = [0, 0]
         played = 0
@@ -546,37 +549,44 @@ def run_b200_arm(args):
                 o = h_out[i % 2]
                 tk = ctypes.c_int64()
                 _lib.check(L.othello_playout_host_async(
-                    ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), P(h_t0), ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX,
-                    None, None, None, P(o[0]), P(o[1]), P(o[2]), P(o[3]), ctypes.byref(tk)), "othello_playout_host_async")
+                    ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), None, ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX,
+                    None, None, None, P(o[2]) if full else None, P(o[3]) if full else None, P(o[4]) if full else None,
+                    None if full else P(o[0]), P(o[1]), ctypes.byref(tk)), "othello_playout_host_async")
                 e2e_gid[0] += G
                 tickets[i % 2] = tk.value
             if i > 0:
                 _lib.check(L.othello_ctx_wait(ctx, tickets[(i - 1) % 2]), "othello_ctx_wait")
-                played += int(h_out[(i - 1) % 2][3][0])                  # the step's result, read on the host
+                played += int(h_out[(i - 1) % 2][1][0])                  # the step's result, read on the host
         return played
 
-    e2e_run(max(3, min(W, 5)))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_positions = e2e_run(K)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    # untimed check of the last batch: per-game results on the host agree with the device-side totals
+    def e2e_timed(full):
+        e2e_run(max(3, min(W, 5)), full)
+        barrier()
+        t0 = time.perf_counter()
+        played = e2e_run(K, full)
+        torch.cuda.synchronize()
+        return played, time.perf_counter() - t0
+
+    e2e_positions, e2e_s = e2e_timed(False)
+    # untimed check of the last batch: the per-game summaries on the host agree with the device-side totals
     last = h_out[(K - 1) % 2]
-    e2e_ok = (int(last[0].sum(dtype=torch.int64)) == int(last[3][0]) and
-              int((last[0] > 0).sum()) == G)
+    sm = last[0].numpy().view("uint16")
+    e2e_ok = (int((sm & 0xff).sum()) == int(last[1][0]) and
+              int((sm >> 8).astype("uint8").view("int8").sum()) == int(last[1][1]) and int((sm & 0xff).min()) > 0)
+    full_positions, full_s = e2e_timed(True)                             # 20 B per game back instead of 2
+    e2e_ok = e2e_ok and int(last[2].sum(dtype=torch.int64)) == int(last[1][0])
     # a single synchronous call (copy-in, kernels, copy-out, wait): the latency of one batch
     sync_ms = []
     for i in range(5):
         t1 = time.perf_counter()
-        _lib.check(L.othello_playout_host(ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), P(h_t0), ops.POLICY_RANDOM, 0, 0, 0, None,
-                                          -1, None, T_MAX, None, None, None, P(last[0]), P(last[1]), P(last[2])),
+        _lib.check(L.othello_playout_host(ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), None, ops.POLICY_RANDOM, 0, 0, 0, None,
+                                          -1, None, T_MAX, None, None, None, P(last[2]), P(last[3]), P(last[4])),
                    "othello_playout_host")
         sync_ms.append(1e3 * (time.perf_counter() - t1))
         e2e_gid[0] += G
     L.othello_ctx_destroy(ctx)
-    h2d = G * (8 + 8 + 1)
-    d2h = G * (4 + 8 + 8) + 32
+    h2d = G * (8 + 8)
+    d2h = G * 2 + 32
 
     # ---- the other two GPU workloads of BASELINE.json, each with its own figures ------------------
     extra = {}
@@ -586,14 +596,14 @@ def run_b200_arm(args):
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s * 1e3, full_s * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([positions, games, e2e_positions], dtype=torch.float64, device=dev)
+        c = torch.tensor([positions, games, e2e_positions, full_positions], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-        positions, games, e2e_positions = float(c[0]), float(c[1]), float(c[2])
+        total_ms, e2e_ms, full_ms = float(t[0]), float(t[1]), float(t[2])
+        positions, games, e2e_positions, full_positions = float(c[0]), float(c[1]), float(c[2]), float(c[3])
     else:
-        e2e_ms = e2e_s * 1e3
+        e2e_ms, full_ms = e2e_s * 1e3, full_s * 1e3
 
     if rank == 0:
         value = positions / (total_ms * 1e-3)
@@ -656,9 +666,14 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": d2h, "games_per_s": G * K * n_gpus / (e2e_ms * 1e-3),
                     "ms_per_step": e2e_ms / K, "frac_of_value": (e2e_positions / e2e_ms) / (positions / total_ms),
                     "sync_call_ms": min(sync_ms), "results_checked": bool(e2e_ok), "host_binding": binding,
+                    "full_results": {"value": full_positions / (full_ms * 1e-3), "unit": UNIT,
+                                     "d2h_bytes_per_step": G * 20 + 32,
+                                     "what": "the same with plies (int32) + final position (2 x u64) per game instead "
+                                             "of the two-byte summary"},
                     "api": "othello_playout_host_async + othello_ctx_wait (C ABI, pinned host buffers, two batches "
-                           "in flight; start positions uploaded and per-game results + totals downloaded every step; "
-                           "trajectories stay in HBM); sync_call_ms = one synchronous othello_playout_host call"},
+                           "in flight; start positions uploaded (16 B per game), two-byte per-game summaries + batch "
+                           "totals downloaded every step; trajectories stay in HBM); sync_call_ms = one synchronous "
+                           "othello_playout_host call returning the full 20 B per game"},
             "gpu_launches": K,
             "step_kernel": step_info,
             "extra": extra,

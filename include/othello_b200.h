@@ -137,6 +137,10 @@ typedef struct {
      * this launch: [0] plies played, [1] sum of (n_black - n_white) as two's complement, [2] games Black
      * won, [3] games White won.  DEVICE uint64[4] or NULL; the caller zeroes it. */
     unsigned long long *totals;
+    /* the same per game, in two bytes: low byte = plies played (saturating at 255), high byte = n_black -
+     * n_white as int8 -- all that store_batch_stats needs of a game (learn_base.py:70-98), and a tenth of
+     * the bytes of nplies + the final position when results cross PCIe.  DEVICE uint16[n] or NULL. */
+    uint16_t *summary;
 } othello_playout_args;
 
 int othello_playout(const othello_playout_args *args, void *stream);
@@ -307,8 +311,9 @@ int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t
 
 /* The same, asynchronous: enqueues copy-in, kernels and copy-out and returns at once with a ticket;
  * the host output arrays (and `totals`: HOST int64[4], the sums of othello_playout_args.totals for
- * this batch, or NULL) are valid after othello_ctx_wait(ctx, ticket).  nplies / final_* may be NULL
- * when the caller only wants `totals` or the device trajectory.  A context keeps two batches in
+ * this batch, or NULL) are valid after othello_ctx_wait(ctx, ticket).  nplies / final_* / summary may each
+ * be NULL: a caller that only needs who won and how long the games were takes `summary` (2 B per game
+ * instead of 20), or just `totals`.  A context keeps two batches in
  * flight: issue batch i+1, then wait for batch i, and the PCIe copies of one batch run under the
  * kernels of the other.  Input arrays must stay untouched until the ticket has been waited for (use
  * pinned memory -- pageable buffers make the copies synchronous).  Issuing a third batch reuses the
@@ -319,6 +324,7 @@ int othello_playout_host_async(othello_ctx *ctx, uint64_t seed, uint64_t gid0, i
                                const float *weights, int32_t policy_white, const float *weights_white, int32_t t_max,
                                uint64_t *traj_black, uint64_t *traj_white, uint8_t *traj_move,
                                int32_t *nplies, uint64_t *final_black, uint64_t *final_white,
+                               uint16_t *summary /* host [n], see othello_playout_args.summary, or NULL */,
                                int64_t *totals, int64_t *ticket);
 int othello_ctx_wait(othello_ctx *ctx, int64_t ticket);
 

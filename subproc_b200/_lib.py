@@ -31,7 +31,7 @@ class PlayoutArgs(ctypes.Structure):
         ("weights", vp), ("t_max", i32), ("stride", i64),
         ("traj_black", vp), ("traj_white", vp), ("traj_move", vp),
         ("nplies", vp), ("final_black", vp), ("final_white", vp),
-        ("policy_white", i32), ("games_per_warp", i32), ("weights_white", vp), ("totals", vp),
+        ("policy_white", i32), ("games_per_warp", i32), ("weights_white", vp), ("totals", vp), ("summary", vp),
     ]
 
 
@@ -89,7 +89,7 @@ SIGNATURES = {
     "othello_playout_host": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32, i32,
                                             vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     "othello_playout_host_async": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, i64, vp, vp, vp, i32, i32, i32,
-                                                  i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp,
+                                                  i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                                   ctypes.POINTER(i64)]),
     "othello_ctx_wait": (ctypes.c_int, [vp, i64]),
     "othello_ctx_set_option": (ctypes.c_int, [vp, i32, i64]),

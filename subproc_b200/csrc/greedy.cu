@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                 a.final_black[g] = fb;
                 a.final_white[g] = fw;
                 plies = t; n_black = __popcll(fb); n_white = __popcll(fw);
+                if (a.summary) a.summary[g] = game_summary(plies, n_black, n_white);
             }
         }
         const bool moving = !done && legal != 0;              // otherwise: finished, or this ply is a pass

@@ -283,7 +283,7 @@ int othello_playout_host_async(othello_ctx *c, uint64_t seed, uint64_t gid0, int
                                int32_t n_rand_black, int32_t n_rand_white, const float *weights, int32_t policy_white,
                                const float *weights_white, int32_t t_max, uint64_t *traj_black, uint64_t *traj_white,
                                uint8_t *traj_move, int32_t *nplies, uint64_t *final_black, uint64_t *final_white,
-                               int64_t *totals, int64_t *ticket)
+                               uint16_t *summary, int64_t *totals, int64_t *ticket)
 {
     OB_CHECK_ARGS(c && n >= 0 && t_max >= 0 && ticket);
     *ticket = 0;                                         // ticket 0 = nothing to wait for
@@ -296,12 +296,13 @@ int othello_playout_host_async(othello_ctx *c, uint64_t seed, uint64_t gid0, int
     othello_slot *sl = &c->slot[si_slot];
     const size_t row8 = align256((size_t)n * 8), row1 = align256((size_t)n);
     const size_t tb_bytes = align256((size_t)(t_max + 1) * n * 8), tm_bytes = align256((size_t)t_max * n + 1);
-    int rc = reserve(c, sl, 4 * row8 + row1 + align256((size_t)n * 4) + 3 * 256 + 2 * tb_bytes + tm_bytes);
+    int rc = reserve(c, sl, 4 * row8 + row1 + align256((size_t)n * 4) + align256((size_t)n * 2) + 3 * 256 + 2 * tb_bytes + tm_bytes);
     if (rc) return rc;
     Carver k = {sl->ws, 0};
     uint64_t *d_b0 = k.take<uint64_t>(n), *d_w0 = k.take<uint64_t>(n), *d_fb = k.take<uint64_t>(n), *d_fw = k.take<uint64_t>(n);
     uint8_t *d_t0 = k.take<uint8_t>(n);
     int32_t *d_np = k.take<int32_t>(n);
+    uint16_t *d_sum = k.take<uint16_t>(n);
     float *d_wt = k.take<float>(OTHELLO_PHASES * OTHELLO_WEIGHTS), *d_wt2 = k.take<float>(OTHELLO_PHASES * OTHELLO_WEIGHTS);
     unsigned long long *d_tot = k.take<unsigned long long>(4);
     uint64_t *d_tb = k.take<uint64_t>((size_t)(t_max + 1) * n), *d_tw = k.take<uint64_t>((size_t)(t_max + 1) * n);
@@ -342,8 +343,10 @@ int othello_playout_host_async(othello_ctx *c, uint64_t seed, uint64_t gid0, int
         a.traj_black = d_tb + c0; a.traj_white = d_tw + c0; a.traj_move = d_tm + c0;
         a.nplies = d_np + c0; a.final_black = d_fb + c0; a.final_white = d_fw + c0;
         a.totals = totals ? d_tot : nullptr;
+        a.summary = summary ? d_sum + c0 : nullptr;
         rc = othello_playout(&a, st);
         if (rc) return fail(c, rc);
+        if (summary) OBH_TRY(cudaMemcpyAsync(summary + c0, d_sum + c0, m * 2, cudaMemcpyDeviceToHost, st));
         if (nplies) OBH_TRY(cudaMemcpyAsync(nplies + c0, d_np + c0, m * 4, cudaMemcpyDeviceToHost, st));
         if (final_black) {
             OBH_TRY(cudaMemcpyAsync(final_black + c0, d_fb + c0, m * 8, cudaMemcpyDeviceToHost, st));
@@ -399,7 +402,7 @@ int othello_playout_host(othello_ctx *c, uint64_t seed, uint64_t gid0, int64_t n
     int64_t ticket = 0;
     int rc = othello_playout_host_async(c, seed, gid0, n, black0, white0, turn0, policy, random_plies, n_rand_black,
                                         n_rand_white, weights, policy_white, weights_white, t_max, traj_black, traj_white,
-                                        traj_move, nplies, final_black, final_white, nullptr, &ticket);
+                                        traj_move, nplies, final_black, final_white, nullptr, nullptr, &ticket);
     if (rc) return rc;
     return othello_ctx_wait(c, ticket);
 }

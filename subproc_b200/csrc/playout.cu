@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_pla
         a.final_black[gi] = fb;
         a.final_white[gi] = fw;
         plies = g.t; n_black = __popcll(fb); n_white = __popcll(fw);
+        if (a.summary) a.summary[gi] = game_summary(plies, n_black, n_white);
     }
     __syncwarp();
     add_totals(a.totals, live, plies, n_black, n_white);

@@ -32,6 +32,12 @@ __device__ __forceinline__ bool substitute_now(u32 key, int t, int rest)
     return rest > 0 && ob::rng_below(ob::rng_draw(key, (u32)t, 0u), (u32)rest) == 0;
 }
 
+// othello_playout_args.summary: plies in the low byte, n_black - n_white (int8) in the high byte
+__device__ __forceinline__ uint16_t game_summary(int plies, int n_black, int n_white)
+{
+    return (uint16_t)(min(plies, 255) | (((n_black - n_white) & 0xff) << 8));
+}
+
 // End of a game kernel: what play_a_game reports per game (game_runner.py:194-199), summed over the
 // launch (othello_playout_args.totals).  Every lane of the warp must arrive (live = false for lanes
 // past the batch); one atomic per value per warp.

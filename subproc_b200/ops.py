@@ -207,7 +207,7 @@ class Playout:
 
 def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn0=None, policy=POLICY_RANDOM,
             random_plies=0, n_rand_black=0, n_rand_white=0, weights=None, t_max=T_MAX_DEFAULT, trajectory=True,
-            out=None, policy_white=None, weights_white=None, totals=None, games_per_warp=0):
+            out=None, policy_white=None, weights_white=None, totals=None, games_per_warp=0, summary=None):
     """GameRunner.play_a_game (game_runner.py:165-201) for n_games games in ONE kernel launch.
 
     Game g draws from the counter-based stream (seed, gid0 + g): sharding games over launches or
@@ -244,6 +244,7 @@ def playout(n_games, seed=0, gid0=0, device=None, black0=None, white0=None, turn
     a.final_white = _req(out.final_white, torch.int64, n, "final_white")
     a.totals = _opt(totals, torch.int64, 4, "totals")
     a.games_per_warp = games_per_warp                          # greedy engine: 0 = chosen from n_games
+    a.summary = _opt(summary, torch.int16, n, "summary")        # per game: plies | (n_black - n_white) << 8
     with torch.cuda.device(device):
         _lib.check(_lib.lib().othello_playout(ctypes.byref(a), _stream(out.nplies)), "othello_playout")
     return out

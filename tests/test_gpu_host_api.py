@@ -106,7 +106,8 @@ def test_playout_host_async_two_batches_in_flight(ctx):
     L = _lib.lib()
     n = 200000 + 3
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-    bufs = [(pin(n, torch.int32), pin(n, torch.int64), pin(n, torch.int64), pin(4, torch.int64)) for _ in range(2)]
+    bufs = [(pin(n, torch.int32), pin(n, torch.int64), pin(n, torch.int64), pin(4, torch.int64), pin(n, torch.int16))
+            for _ in range(2)]
     T = lambda t: ctypes.c_void_p(t.data_ptr())
     b0 = pin(n, torch.int64).fill_(ops.signed64(ops.START_BLACK))
     w0 = pin(n, torch.int64).fill_(ops.signed64(ops.START_WHITE))
@@ -118,7 +119,7 @@ def test_playout_host_async_two_batches_in_flight(ctx):
             tk = ctypes.c_int64()
             up = (T(b0), T(w0)) if i % 2 else (None, None)        # with and without uploaded start positions
             assert L.othello_playout_host_async(ctx, 21, 1000 * i, n, up[0], up[1], None, 0, 0, 0, 0, None, -1, None, 120,
-                                                None, None, None, T(o[0]), T(o[1]), T(o[2]), T(o[3]), ctypes.byref(tk)) == 0
+                                                None, None, None, T(o[0]), T(o[1]), T(o[2]), T(o[4]), T(o[3]), ctypes.byref(tk)) == 0
             assert tk.value > 0
             tickets[i % 2] = tk.value
         if i > 0:
@@ -131,13 +132,17 @@ def test_playout_host_async_two_batches_in_flight(ctx):
             c = po.final_counts().cpu().numpy().astype(np.int64)
             assert o[3].tolist() == [int(po.nplies.sum()), int((c[:, 0] - c[:, 1]).sum()),
                                      int((c[:, 0] > c[:, 1]).sum()), int((c[:, 1] > c[:, 0]).sum())]
+            # the two-byte summary: plies in the low byte, n_black - n_white (int8) in the high byte
+            sm = o[4].numpy().view(np.uint16)
+            assert np.array_equal(sm & 0xff, po.nplies.cpu().numpy()) and \
+                np.array_equal((sm >> 8).astype(np.uint8).view(np.int8), (c[:, 0] - c[:, 1]).astype(np.int8))
     assert L.othello_ctx_wait(ctx, tickets[0]) == 0 and L.othello_ctx_wait(ctx, 0) == 0      # waiting twice is harmless
     assert L.othello_ctx_wait(ctx, 10 ** 9) == -1                                            # a ticket never issued
     # totals only
     tot = pin(4, torch.int64)
     tk = ctypes.c_int64()
     assert L.othello_playout_host_async(ctx, 21, 0, n, None, None, None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
-                                        None, None, None, T(tot), ctypes.byref(tk)) == 0
+                                        None, None, None, None, T(tot), ctypes.byref(tk)) == 0
     assert L.othello_ctx_wait(ctx, tk.value) == 0
     assert int(tot[0]) == int(ops.playout(n, seed=21, gid0=0, device=DEV, trajectory=False).nplies.sum())
     assert L.othello_ctx_set_option(ctx, 1, 4) == 0 and L.othello_ctx_set_option(ctx, 99, 1) == -1

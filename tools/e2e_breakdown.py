@@ -92,7 +92,8 @@ def main():
     h_b0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_BLACK))
     h_w0 = pin(G, torch.int64).fill_(ops.signed64(ops.START_WHITE))
     h_t0 = pin(G, torch.uint8).fill_(ops.BLACK)
-    bufs = [(pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64), pin(4, torch.int64)) for _ in range(2)]
+    bufs = [(pin(G, torch.int32), pin(G, torch.int64), pin(G, torch.int64), pin(4, torch.int64), pin(G, torch.int16))
+            for _ in range(2)]
     d_b0, d_w0, d_t0 = h_b0.to(dev), h_w0.to(dev), h_t0.to(dev)
     d_np, d_fb, d_fw = po.nplies, po.final_black, po.final_white
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -138,7 +139,7 @@ def main():
     out["sync_plus_torch_sum_ms"] = wall(lambda i: sync_call(i, "torch"))       # round 1's bench loop
     out["sync_plus_numpy_sum_ms"] = wall(lambda i: sync_call(i, "numpy"))
 
-    def async_loop(reps, upload=True, per_game=True, totals=True):
+    def async_loop(reps, upload=True, per_game=True, totals=True, summary=False, turn=True):
         """two batches in flight: issue i+1, wait i.  returns ms per batch (this rank)"""
         tickets = [None, None]
         total = 0
@@ -149,9 +150,9 @@ def main():
                 tk = ctypes.c_int64()
                 _lib.check(L.othello_playout_host_async(
                     ctx, 1, gid[0], G, P(h_b0) if upload else None, P(h_w0) if upload else None,
-                    P(h_t0) if upload else None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
+                    P(h_t0) if upload and turn else None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
                     P(b[0]) if per_game else None, P(b[1]) if per_game else None, P(b[2]) if per_game else None,
-                    P(b[3]) if totals else None, ctypes.byref(tk)), "playout_host_async")
+                    P(b[4]) if summary else None, P(b[3]) if totals else None, ctypes.byref(tk)), "playout_host_async")
                 gid[0] += G
                 tickets[i % 2] = tk.value
             if i > 0:
@@ -169,6 +170,8 @@ def main():
     out["async_positions_per_step"] = tot / K
     out["async_no_upload_ms"], _ = timed_async(upload=False)
     out["async_totals_only_ms"], _ = timed_async(upload=False, per_game=False)
+    out["async_upload_summary_ms"], _ = timed_async(upload=True, per_game=False, summary=True, turn=False)   # 16 B in, 2 B out per game
+    out["async_summary_only_ms"], _ = timed_async(upload=False, per_game=False, summary=True)
     for ch in (1, 2, 4, 16):
         _lib.check(L.othello_ctx_set_option(ctx, 1, ch), "set_option")
         out["async_chunks%d_ms" % ch], _ = timed_async()
