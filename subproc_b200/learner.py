@@ -344,6 +344,34 @@ class ProgressPositionMovesLearn(object):
         self.last_processed_id = last_book_id
         return mses, scores, params, nsamples
 
+    def self_play_iteration_table(self, n_games, seed=0, iteration=0, random_plies=10, device=None, t_max=120,
+                                  sample=50000):
+        """One learning iteration with the REFERENCE's learning semantics (single GPU): greedy self-play with the
+        current weights, every (position, side) smooths the order-dependent value table in the reference's order
+        (progress_position_moves_learn.py:37-62,88-91), then each shard is refitted on a sample of <= 50 000
+        distinct table entries (:66-86,160-184) and stored with int() truncation (:196-209).
+        Returns (playout, (mses, scores, params, nsamples))."""
+        import torch
+        from . import ops, value_table
+        dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        if getattr(self, 'table', None) is None:
+            self.table = value_table.ValueTable(device=dev, a=self.a, lam=self.l)
+        w = torch.from_numpy(self.weights_table()).to(dev)
+        gid0 = iteration * n_games
+        po = ops.playout(n_games, seed=seed, gid0=gid0, device=dev, policy=ops.POLICY_GREEDY,
+                         random_plies=random_plies, weights=w, t_max=t_max)
+        self.table.update_from_playout(po)
+        old = np.asarray(self.read_parameters()[1:], dtype=np.float64).reshape(4, 9)
+        mses, scores, params, nsamples = [], [], [], []
+        for s, (lo, hi) in enumerate(PHASE_SHARDS):
+            mse, score, param, nsample = self.table.fit_parameter(lo, hi, num=sample, seed=seed + 4 * iteration + s)
+            if nsample == 0:
+                param = tuple(float(v) for v in old[s])
+            mses.append(mse); scores.append(score); params.append(param); nsamples.append(nsample)
+        self.params = stored_parameters(params)
+        self.last_processed_id = gid0 + n_games - 1
+        return po, (mses, scores, params, nsamples)
+
     def self_play_iteration(self, games_per_rank, seed=0, iteration=0, random_plies=10, device=None, rank=0,
                             world=1, t_max=120):
         """config 5: greedy self-play with the current weights on this rank's shard of game ids,

@@ -145,3 +145,20 @@ def test_learner_checkpoint_round_trip(tmp_path):
     A.learn_and_update_batch(bks[20:], device=DEV, sample=500, seed=9)
     B.learn_and_update_batch(bks[20:], device=DEV, sample=500, seed=9)
     assert B.table.items() == A.table.items() and B.read_parameters() == A.read_parameters()
+
+
+def test_self_play_iteration_with_the_references_table_semantics():
+    """greedy self-play -> exact value table -> per-shard fit on samples of the table, iterated: the table carries
+    over, the parameters stay in the stored range, and the table equals one built from the same games directly"""
+    from subproc_b200 import learner
+    L = learner.ProgressPositionMovesLearn(); L.configure({})
+    po0, (mses, scores, params, nsamples) = L.self_play_iteration_table(3000, seed=41, iteration=0, device=DEV, sample=5000)
+    assert len(params) == 4 and all(len(p) == 9 for p in params) and sum(nsamples) > 0
+    rp0 = L.read_parameters()
+    assert rp0[0] == 2 and all(-127 <= v <= 127 for v in rp0[1:])
+    n0 = len(L.table)
+    po1, _ = L.self_play_iteration_table(3000, seed=41, iteration=1, device=DEV, sample=5000)
+    assert len(L.table) > n0 and L.last_processed() == 5999
+    vt = value_table.ValueTable(device=DEV)
+    vt.update_from_playout(po0); vt.update_from_playout(po1)
+    assert vt.items() == L.table.items()
