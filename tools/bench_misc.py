@@ -47,12 +47,19 @@ ms = timed(lambda: ops.learn_accumulate(po)); out.append(("othello_learn_accumul
 for d in (9, 10, 11):
     t0 = time.perf_counter(); nodes = ops.perft(d, device=dev); dt = time.perf_counter() - t0
     t0 = time.perf_counter(); nodes = ops.perft(d, device=dev); dt = min(dt, time.perf_counter() - t0)
-    out.append(("othello_perft(%d)=%d" % (d, nodes), nodes / dt, "nodes/s (wall, incl. host sync per level)", None))
+    ms = timed(lambda: ops.perft_part(d, 0, 1, device=dev), reps=3)            # the launch sequence alone, result left on the device
+    out.append(("othello_perft(%d)=%d" % (d, nodes), nodes / dt, "nodes/s (wall, one synchronous call)", None))
+    out.append(("othello_perft_async(%d)" % d, nodes / ms * 1e3, "nodes/s (device time of the launch sequence: %.3f ms)" % ms, None))
 small = ops.playout(1 << 16, seed=2, gid0=0, device=dev)
 vt = value_table.ValueTable(device=dev)
 torch.cuda.synchronize(); t0 = time.perf_counter(); nrec = vt.update_from_playout(small); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-out.append(("value_table.update(65536 games)", nrec / dt, "records/s (wall, incl. sort)", None))
+out.append(("value_table.update(65536 games), first batch into an empty table", nrec / dt, "records/s (wall, incl. allocating the table)", None))
+dts = []
+for _ in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); nrec = vt.update_from_playout(small); torch.cuda.synchronize()
+    dts.append(time.perf_counter() - t0)
+out.append(("value_table.update(65536 games)", nrec / min(dts), "records/s (wall: records + sort + probe + apply)", None))
 # the HBM-bound codecs and batch rules at a size where launch latency no longer matters (2^24 positions)
 big = 1 << 24
 rep = big // n
