@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/run_all_configs.py -- the five BASELINE.json configs, each checked and timed on ONE GPU
+"""tests/run_all_configs.py -- the five BASELINE.json configs, each checked and timed on ONE GPU
 (configs 4/5 at their per-GPU size; tools/bench_configs.py runs them over torchrun for N GPUs).
 Prints one JSON object; `parity` entries are checked against the oracle / golden vectors here."""
 import gzip

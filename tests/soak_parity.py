@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/soak_parity.py -- long differential run: GPU playouts vs the oracle, bit for bit, on far more
+"""tests/soak_parity.py -- long differential run: GPU playouts vs the oracle, bit for bit, on far more
 games than the test suite plays (random, go_for substitution, greedy, mixed engines, custom starts)."""
 import os
 import sys

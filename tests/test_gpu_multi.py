@@ -26,7 +26,8 @@ def _worker(rank, world, port, q):
     acc = ops.learn_accumulate(po)
     L = learner.ProgressPositionMovesLearn()
     rows = L.learn_from_acc(acc)                                 # all-reduce of the int64 accumulators inside
-    q.put((rank, po.nplies.cpu().numpy(), ops.bits_numpy(po.final_black), acc.cpu().numpy(), L.read_parameters()))
+    nodes = ops.perft_distributed(10, device=dev)               # depth-first stage split over the ranks, one u64 all-reduce
+    q.put((rank, po.nplies.cpu().numpy(), ops.bits_numpy(po.final_black), acc.cpu().numpy(), L.read_parameters(), nodes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,6 +55,7 @@ def test_two_ranks_equal_one_gpu_on_the_union_of_games():
     for g in got:                                                  # every rank holds the all-reduced accumulators:
         assert np.array_equal(g[3], whole.cpu().numpy())           # exact integer sums, the same bits as one GPU
     assert got[0][4] == got[1][4]                                  # identical parameters on all ranks
+    assert got[0][5] == got[1][5] == 24571284                      # perft(10), SURVEY.md section 4
     L = learner.ProgressPositionMovesLearn()
     L.learn_from_acc(whole)
     assert L.read_parameters() == got[0][4]                        # ... and identical to the single-GPU fit
