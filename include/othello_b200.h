@@ -317,7 +317,7 @@ int othello_playout_host(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t
  * flight: issue batch i+1, then wait for batch i, and the PCIe copies of one batch run under the
  * kernels of the other.  Input arrays must stay untouched until the ticket has been waited for (use
  * pinned memory -- pageable buffers make the copies synchronous).  Issuing a third batch reuses the
- * device buffers of the first (stream-ordered; the caller need not have waited for it). */
+ * device buffers of the first; if the caller has not waited for the first yet, the call does. */
 int othello_playout_host_async(othello_ctx *ctx, uint64_t seed, uint64_t gid0, int64_t n_games,
                                const uint64_t *black0, const uint64_t *white0, const uint8_t *turn0,
                                int32_t policy, int32_t random_plies, int32_t n_rand_black, int32_t n_rand_white,

@@ -307,9 +307,11 @@ int othello_playout_host_async(othello_ctx *c, uint64_t seed, uint64_t gid0, int
     unsigned long long *d_tot = k.take<unsigned long long>(4);
     uint64_t *d_tb = k.take<uint64_t>((size_t)(t_max + 1) * n), *d_tw = k.take<uint64_t>((size_t)(t_max + 1) * n);
     uint8_t *d_tm = k.take<uint8_t>((size_t)t_max * n + 1);
-    // the slot's previous batch (two tickets ago) ended on this very stream: stream order protects the
-    // device buffers, no host wait needed
+    // The slot's previous batch (two tickets ago) ended on this very stream, so stream order already
+    // protects the device buffers.  If the caller never waited for that batch, wait for it now: once its
+    // slot has been reused, an old ticket must mean "complete" to othello_ctx_wait.
     cudaStream_t s = sl->ctl;
+    if (sl->pending) { OBH_TRY(cudaEventSynchronize(sl->done)); sl->pending = false; }
     if (weights) OBH_TRY(cudaMemcpyAsync(d_wt, weights, sizeof(float) * OTHELLO_PHASES * OTHELLO_WEIGHTS, cudaMemcpyHostToDevice, s));
     if (weights_white) OBH_TRY(cudaMemcpyAsync(d_wt2, weights_white, sizeof(float) * OTHELLO_PHASES * OTHELLO_WEIGHTS, cudaMemcpyHostToDevice, s));
     if (totals) OBH_TRY(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), s));
@@ -381,7 +383,7 @@ int othello_ctx_wait(othello_ctx *c, int64_t ticket)
     OB_CHECK_ARGS(c && ticket >= 0 && ticket < c->next_ticket);
     if (ticket == 0) return 0;
     othello_slot *sl = &c->slot[ticket % kSlots];
-    // an older ticket of this slot completed before the slot was reused (stream order)
+    // an older ticket of this slot was completed (waited for) when the slot was reused
     if (sl->pending && sl->ticket == ticket) {
         OB_CUDA(cudaSetDevice(c->device));
         OB_CUDA(cudaEventSynchronize(sl->done));

@@ -149,3 +149,21 @@ def test_playout_host_async_two_batches_in_flight(ctx):
     # the synchronous small-batch calls still work while nothing is pending, and after a playout
     own = np.array([ops.START_BLACK], np.uint64); opp = np.array([ops.START_WHITE], np.uint64); out = np.zeros(1, np.uint64)
     assert L.othello_legal_host(ctx, P(own), P(opp), P(out), 1) == 0 and int(out[0]) == 0x0000102004080000
+
+
+def test_three_batches_issued_before_any_wait(ctx):
+    """a third batch reuses the first one's slot: the call completes the first, and its old ticket still waits fine"""
+    L = _lib.lib()
+    n = 70000
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    T = lambda t: ctypes.c_void_p(t.data_ptr())
+    outs = [pin(n, torch.int32) for _ in range(3)]
+    tks = []
+    for i in range(3):
+        tk = ctypes.c_int64()
+        assert L.othello_playout_host_async(ctx, 5, 10 * i, n, None, None, None, 0, 0, 0, 0, None, -1, None, 120, None, None,
+                                            None, T(outs[i]), None, None, None, None, ctypes.byref(tk)) == 0
+        tks.append(tk.value)
+    for i in (0, 2, 1):
+        assert L.othello_ctx_wait(ctx, tks[i]) == 0
+        assert torch.equal(outs[i], ops.playout(n, seed=5, gid0=10 * i, device=DEV, trajectory=False).nplies.cpu())
