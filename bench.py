@@ -330,7 +330,18 @@ def config4_extra(dev, rank, world, G=1 << 19, reps=5, random_plies=10):
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     sec = float(tmax[0]) * 1e-3
-    return {"workload": "config4_greedy_selfplay", "games_per_gpu": G, "random_plies": random_plies, "launches": reps,
+    executed = None
+    kp = os.path.join(ROOT, "profiles", "greedy_kernel_costs.json")
+    if os.path.isfile(kp):
+        kc = json.load(open(kp))
+        rate = float(v[2]) / world / (sec * 1e3)                         # children per ms per GPU, this run
+        executed = {"source": "profiles/greedy_kernel_costs.json (ncu --set full of one launch: %s)" % kc["source"],
+                    "thread_inst_per_child": kc["thread_inst_per_child"], "active_lanes_per_inst": kc["active_lanes_per_inst"],
+                    "alu_pipe_pct_ncu": kc["alu_pipe_pct"], "fmaheavy_pipe_pct_ncu": kc["fmaheavy_pipe_pct"],
+                    "xu_pipe_pct_ncu": kc["xu_pipe_pct"], "issue_slot_pct_ncu": kc["issue_slot_pct"],
+                    "alu_pipe_frac_at_this_runs_rate": kc["alu_pipe_pct"] / 100.0 * rate / kc["children_per_ms_under_ncu"],
+                    "thread_inst_per_s": float(v[2]) / sec * kc["thread_inst_per_child"]}
+    return {"workload": "config4_greedy_selfplay", "roofline": {"bound": "int32 ALU pipe", "executed": executed}, "games_per_gpu": G, "random_plies": random_plies, "launches": reps,
             "weights": "default_value() rows", "kernel_ms": float(tmax[0]) / reps,
             "positions_per_s": float(v[0]) / sec, "games_per_s": float(v[1]) / sec,
             "children_per_s": float(v[2]) / sec,
