@@ -48,6 +48,24 @@ def test_argument_validation_needs_no_gpu():
     assert L.othello_perft(0x0000000810000000, 0x0000001008000000, 1, 0, None, 0, ctypes.byref(res), None) == 0
     assert res.value == 1
     assert L.othello_perft(0, 0, 3, 2, None, 0, ctypes.byref(res), None) == -1
+    # round-2 entry points: bad arguments are refused before anything touches a device
+    assert L.othello_perft_async(0, 0, 1, 3, 2, 2, None, 0, None, None) == -1            # part >= nparts, no result
+    assert L.othello_learn_accumulate(None, None, None, None, None, 5, 5, 120, None, None, None) == -1
+    assert L.othello_learn_stats(None, None, None) == -1 and L.othello_learn_refit(None, 1, None, None, None, None, None, None) == -1
+    assert L.othello_sort_records(None, None, None, None, 0, 43, None, 0, None) == 0     # nothing to sort
+    assert L.othello_sort_records(None, None, None, None, 10, 43, None, 0, None) == -1
+    assert L.othello_sort_records(None, None, None, None, 10, 0, None, 0, None) == -1    # key_bits out of range
+    assert L.othello_partition_records(None, None, None, None, 4, 300, None, None, 0, None) == -1   # world > 256
+    assert L.othello_table_probe(None, -1, None, None, 20, None, 0, None, None) == -1
+    assert L.othello_table_apply(None, None, 0, 0.03, None, None, 20, None, None, 0, None, None) == 0
+    assert L.othello_table_rehash(None, 10, None, None, 3, None) == -1                   # 10 keys do not fit 8 slots at load 1/2
+    assert L.othello_sort_workspace_bytes(1 << 20) >= 256 * 256 * 4 and L.othello_table_workspace_bytes(0) > 0
+    assert L.othello_perft_workspace_bytes(2) < L.othello_perft_workspace_bytes(6) <= L.othello_perft_workspace_bytes(40)
+    tk = ctypes.c_int64(7)
+    assert L.othello_playout_host_async(None, 0, 0, 4, None, None, None, 0, 0, 0, 0, None, -1, None, 120, None, None, None,
+                                        None, None, None, None, None, ctypes.byref(tk)) == -1
+    assert L.othello_ctx_wait(None, 0) == -1 and L.othello_ctx_set_option(None, 1, 4) == -1
+    assert L.othello_board_apply_host(None, 0, 0, 1, 0, None) == -1
 
 
 def test_product_never_imports_the_oracle_or_the_reference():
