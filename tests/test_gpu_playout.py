@@ -189,8 +189,13 @@ def test_greedy_games_do_not_depend_on_games_per_warp(oracle):
     outs = []
     for gpw in (32, 16, 8, 0):
         tot = torch.zeros(4, dtype=torch.int64, device=DEV)
+        sm = torch.zeros(n, dtype=torch.int16, device=DEV)
         po = ops.playout(n, seed=19, gid0=40, device=DEV, policy=ops.POLICY_GREEDY, random_plies=6, n_rand_black=2,
-                         n_rand_white=1, weights=w, games_per_warp=gpw, totals=tot)
+                         n_rand_white=1, weights=w, games_per_warp=gpw, totals=tot, summary=sm)
+        c = po.final_counts().cpu().numpy().astype(np.int64)
+        smv = sm.cpu().numpy().view(np.uint16)
+        assert np.array_equal(smv & 0xff, po.nplies.cpu().numpy())
+        assert np.array_equal((smv >> 8).astype(np.uint8).view(np.int8), (c[:, 0] - c[:, 1]).astype(np.int8))
         assert np.array_equal(po.nplies[:600].cpu().numpy(), ref['nplies'])
         assert np.array_equal(ops.bits_numpy(po.final_black[:600]), ref['final_black'])
         t = 30
