@@ -205,3 +205,26 @@ def test_greedy_games_do_not_depend_on_games_per_warp(oracle):
         outs.append((po.nplies.clone(), po.final_black.clone(), po.final_white.clone(), tot))
     for o in outs[1:]:
         assert all(torch.equal(x, y) for x, y in zip(o, outs[0]))
+
+
+def test_greedy_with_float_weights_how_often_fp32_and_fp64_disagree(oracle):
+    """Greedy games are bit-exact for integer-valued weights (the stored form).  With arbitrary float weights the
+    device evaluates in fp32 and the oracle in fp64: scores agree to 1e-5 relative, so a game can only differ where
+    two successors are closer than that.  Count it: weights with three decimals (ties at the 1e-3 level are then
+    real ties in both precisions, anything closer is rounding), 4000 games of ~50 greedy plies each."""
+    rng = np.random.RandomState(11)
+    wts = np.zeros((4, 10))
+    wts[:, :9] = np.round(rng.uniform(-60, 100, size=(4, 9)), 3)
+    wts[:, 9] = np.round(rng.uniform(-5, 5, size=4), 3)
+    n = 4000
+    ref = oracle.playout(29, 0, n, policy=1, random_plies=10, weights=wts)
+    po = ops.playout(n, seed=29, gid0=0, device=DEV, policy=ops.POLICY_GREEDY, random_plies=10,
+                     weights=torch.from_numpy(wts.astype(np.float32)).to(DEV))
+    same = (po.nplies.cpu().numpy() == ref['nplies']) & (ops.bits_numpy(po.final_black) == ref['final_black']) & \
+           (ops.bits_numpy(po.final_white) == ref['final_white'])
+    # first ply at which a differing game leaves the oracle's move list
+    mv = po.move.cpu().numpy()
+    first = [int(np.argmax(mv[:ref['nplies'][g], g] != ref['move'][:ref['nplies'][g], g])) for g in np.flatnonzero(~same)]
+    print("float weights: %d of %d games identical; differing games first diverge at plies %s" % (same.sum(), n, sorted(first)[:10]))
+    assert same.mean() >= 0.99
+    assert all(t >= 10 for t in first)                         # never inside the random opening
