@@ -30,11 +30,13 @@ struct Game {
 // One ply.  BLACK: 1 = Black moves, 0 = White moves (known at compile time when every game of the
 // launch starts with the same colour: Black and White then alternate strictly, passes included),
 // -1 = read `black_moves`.  Returns false when the game is over.
-template <bool TRAJ, int BLACK>
+// TRAJ: 0 = no trajectory, 1 = trajectory with capacity checks, 2 = trajectory that is known to fit (standard
+// opening and t_max >= 120: 60 moves + at most 60 interleaved passes), so the two checks per ply fall away.
+template <int TRAJ, int BLACK>
 __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int t_max, int64_t stride, const Rays &rays)
 {
     const bool bm = BLACK < 0 ? black_moves : (BLACK == 1);
-    if (TRAJ && g.t <= t_max) {
+    if (TRAJ == 2 || (TRAJ == 1 && g.t <= t_max)) {
         __stcs(g.tb, bm ? g.own : g.opp);
         __stcs(g.tw, bm ? g.opp : g.own);
         g.tb += stride; g.tw += stride;
@@ -55,7 +57,7 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         x = 1ull << move;
         f = obf::flips_for(move, g.own, g.opp, own_r, opp_r, rays);
     }
-    if (TRAJ && g.t < t_max) { __stcs(g.tm, (uint8_t)move); g.tm += stride; }
+    if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) { __stcs(g.tm, (uint8_t)move); g.tm += stride; }
     // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
     const u64 moved = g.own | f | x;
     g.own = g.opp & ~f;
@@ -65,7 +67,7 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
 }
 
 // UNIFORM: no per-game turn0 -- every game starts with Black, so the loop is unrolled over the two colours
-template <bool TRAJ, bool UNIFORM>
+template <int TRAJ, bool UNIFORM>
 // (128 threads x >= 10 CTAs per SM measured best on B200: 64/128/256 threads and 9..12 CTAs are within 2 %)
 __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
 {
@@ -113,11 +115,17 @@ int launch(const othello_playout_args &a, cudaStream_t s)
 {
     const unsigned blocks = ob_blocks(a.n_games, kThreads);
     if (a.traj_black) {
-        if (a.turn0) playout_kernel<true, false><<<blocks, kThreads, 0, s>>>(a);
-        else playout_kernel<true, true><<<blocks, kThreads, 0, s>>>(a);
+        const bool fits = a.black0 == nullptr && a.t_max >= 120;          // every game from the standard opening fits
+        if (a.turn0) {
+            if (fits) playout_kernel<2, false><<<blocks, kThreads, 0, s>>>(a);
+            else playout_kernel<1, false><<<blocks, kThreads, 0, s>>>(a);
+        } else {
+            if (fits) playout_kernel<2, true><<<blocks, kThreads, 0, s>>>(a);
+            else playout_kernel<1, true><<<blocks, kThreads, 0, s>>>(a);
+        }
     } else {
-        if (a.turn0) playout_kernel<false, false><<<blocks, kThreads, 0, s>>>(a);
-        else playout_kernel<false, true><<<blocks, kThreads, 0, s>>>(a);
+        if (a.turn0) playout_kernel<0, false><<<blocks, kThreads, 0, s>>>(a);
+        else playout_kernel<0, true><<<blocks, kThreads, 0, s>>>(a);
     }
     return ob_launch_status();
 }
