@@ -104,17 +104,17 @@ struct Rays {
 // the table is built at compile time and lives in global memory (L2-resident); a CTA copies its 2 KB
 // into shared memory with two loads per thread instead of walking 256 rays
 struct RayTableInit {
-    u64 v[obf::kRayDirs * 64];
+    u64 v[obf::kRayTable64];
     constexpr RayTableInit() : v()
     {
-        for (int i = 0; i < obf::kRayDirs * 64; i++) v[i] = obf::make_ray(i >> 6, i & 63);
+        for (int i = 0; i < obf::kRayTable64; i++) v[i] = obf::make_ray(i >> 6, i & 63);
     }
 };
 static __device__ const RayTableInit kRayTable = RayTableInit();
 
 __device__ __forceinline__ void fill_rays(u64 *t)
 {
-    for (int i = threadIdx.x; i < obf::kRayDirs * 64; i += blockDim.x) t[i] = kRayTable.v[i];
+    for (int i = threadIdx.x; i < obf::kRayTable64; i += blockDim.x) t[i] = kRayTable.v[i];
 }
 
 // Board.put(piece, x, y) (board.py:161-174): flips of an own disc on EMPTY square s

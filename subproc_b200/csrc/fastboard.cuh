@@ -203,8 +203,10 @@ OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp
 // ---- put(): flips through carry propagation along rays -----------------------------------------
 // ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge
 constexpr int kRayDirs = 4;
+constexpr int kRayTable64 = (kRayDirs + 1) * 64;   // table entries: the four ray rows + a row of single-square masks
 OBF_HD constexpr u64 make_ray(int d, int s)
 {
+    if (d == kRayDirs) return 1ull << s;                               // row 4: the square itself (1 << s as a table load)
     const int dx = (d == 0) ? 1 : (d == 1) ? -1 : (d == 2) ? 0 : 1;   // +1: E, +7: SW, +8: S, +9: SE (y grows with s)
     const int dy = (d == 0) ? 0 : 1;
     u64 r = 0;
@@ -270,13 +272,16 @@ __device__ __forceinline__ int kth_set_bit(u64 mask, int k)
 #endif
 
 // Discs flipped by an `own` disc on the EMPTY square s (board.py:161-174); rays = table [4][64].
-template <typename RayTable>
+// BIT_LUT: take the move bit and its rotation from the table's fifth row (two LDS) instead of a variable
+// 64-bit shift (two ALU instructions) + two BREVs.  Pays in the random playout kernel, whose LSU pipe idles
+// (+1.1 %); costs the greedy kernel 0.8 % (its LSU pipe also carries the work-item lists), so it is a choice.
+template <bool BIT_LUT = false, typename RayTable>
 OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTable &rays)
 {
     const int sr = 63 - s;
-    const u64 x = 1ull << s;
 #if defined(__CUDA_ARCH__)
-    const u64 xr = rev64(x);                   // two BREVs on the XU pipe instead of two more ALU shifts
+    const u64 x = BIT_LUT ? rays(kRayDirs, s) : 1ull << s;
+    const u64 xr = BIT_LUT ? rays(kRayDirs, sr) : rev64(x);   // (two BREVs on the XU pipe, not two more ALU shifts)
     const u32 one = kOpaqueOne;
     u32 f_lo = 0, f_hi = 0, r_lo = 0, r_hi = 0;
 #pragma unroll
@@ -286,7 +291,7 @@ OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTab
     }
     return pack(f_lo, f_hi) | rev64(pack(r_lo, r_hi));
 #else
-    const u64 xr = 1ull << sr;
+    const u64 x = 1ull << s, xr = 1ull << sr;
     u64 f = 0, fr = 0;
     for (int d = 0; d < kRayDirs; d++) {
         f |= ray_flips(x, rays(d, s), own, opp);

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
 {
     constexpr int kW = OTHELLO_PHASES * OTHELLO_WEIGHTS;
     __shared__ float w_s[2 * kW];                             // Black's table, then White's
-    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    __shared__ u64 ray_s[obf::kRayTable64];
     __shared__ WarpScratch scratch[kWarps];
     for (int i = threadIdx.x; i < 2 * kW; i += blockDim.x) {    // (a CTA is 2 or 4 warps, see ob_launch_greedy)
         const float *src = i < kW ? (a.weights ? a.weights : a.weights_white)

@@ -54,8 +54,8 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         // random one; behind a random engine both draw the same k-th move from stream 1, so the
         // budgets n_rand_* do not change any game played by this kernel.
         move = obf::kth_set_bit(legal, (int)rng_below(r1, (u32)n));
-        x = 1ull << move;
-        f = obf::flips_for(move, g.own, g.opp, own_r, opp_r, rays);
+        x = rays(obf::kRayDirs, move);
+        f = obf::flips_for<true>(move, g.own, g.opp, own_r, opp_r, rays);
     }
     if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) { __stcs(g.tm, (uint8_t)move); g.tm += stride; }
     // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
@@ -71,7 +71,7 @@ template <int TRAJ, bool UNIFORM>
 // (128 threads x >= 10 CTAs per SM measured best on B200: 64/128/256 threads and 9..12 CTAs are within 2 %)
 __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
 {
-    __shared__ u64 ray_s[obf::kRayDirs * 64];
+    __shared__ u64 ray_s[obf::kRayTable64];
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};

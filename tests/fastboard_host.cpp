@@ -2,14 +2,14 @@
 // host so the exact source the kernels use can be compared with the oracle without a GPU.
 #include "../subproc_b200/csrc/fastboard.cuh"
 
-static unsigned long long g_rays[4][64];
+static unsigned long long g_rays[5][64];
 static bool g_init = false;
 struct Rays { unsigned long long operator()(int d, int s) const { return g_rays[d][s]; } };
 
 static void init()
 {
     if (g_init) return;
-    for (int d = 0; d < 4; d++) for (int s = 0; s < 64; s++) g_rays[d][s] = obf::make_ray(d, s);
+    for (int d = 0; d < 5; d++) for (int s = 0; s < 64; s++) g_rays[d][s] = obf::make_ray(d, s);
     g_init = true;
 }
 
