@@ -226,16 +226,20 @@ OBF_HD u64 ray_flips(u64 x, u64 R, u64 own, u64 opp)
 
 #if defined(__CUDACC__)
 // acc += run when the ray is closed.  The flipped runs of the 8 rays are pairwise disjoint, so the
-// OR-accumulation of put() is an ADD; gated by a predicate and issued as IMAD it costs the ALU pipe
-// two instructions (OR of the two halves of `closed`, compare) instead of five.
+// OR-accumulation of put() is an ADD.  `closed` has at most one bit set, so the sum of its two halves is
+// non-zero exactly when the ray is closed; POPC (XU pipe) turns that into 0 / 1 and the run is added through
+// a multiply by it (IMAD, FMA pipe): the test costs the saturated ALU pipe nothing (it used to be an OR of the
+// halves + a compare per ray, 16 ALU instructions per move).
 __device__ __forceinline__ void ray_accumulate(u32 &acc_lo, u32 &acc_hi, u64 x, u64 R, u64 own, u64 opp, u32 one)
 {
     const u64 sum = (opp | ~R) + x;
     const u64 closed = sum & own & R;
     const u64 run = R & opp & ~sum;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p mad.lo.u32 %0, %2, %5, %0;\n\t@p mad.lo.u32 %1, %3, %5, %1;\n\t}"
-        : "+r"(acc_lo), "+r"(acc_hi)
-        : "r"(lo32(run)), "r"(hi32(run)), "r"(lo32(closed) | hi32(closed)), "r"(one));
+    u32 any;
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(any) : "r"(lo32(closed)), "r"(hi32(closed)), "r"(one));
+    const u32 valid = (u32)__popc(any);
+    asm("mad.lo.u32 %0, %2, %4, %0;\n\tmad.lo.u32 %1, %3, %4, %1;"
+        : "+r"(acc_lo), "+r"(acc_hi) : "r"(lo32(run)), "r"(hi32(run)), "r"(valid));
 }
 #endif
 
@@ -255,17 +259,18 @@ __device__ __forceinline__ int kth_set_bit(u64 mask, int k)
             "@p mad.lo.s32 %1, %3, %6, %1;\n\t}"
             : "+r"(v), "+r"(k), "+r"(base) : "r"(c), "r"(hi), "r"(one), "r"(0u - one));
     }
-#define OBF_KTH_STEP(W, M)                                                                                         \
+#define OBF_KTH_STEP(W)                                                                                            \
     {                                                                                                              \
-        const int c = __popc(v & (M));                                                                             \
+        /* set bits among the low W of the window: shifted to the top (IMAD.SHL, FMA pipe) instead of masked (LOP3) */ \
+        const int c = __popc(v << (32 - (W)));                                                                     \
         asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, %3;\n\t@p shr.u32 %0, %0, " #W ";\n\t"                        \
             "@p mad.lo.s32 %2, %4, " #W ", %2;\n\t@p mad.lo.s32 %1, %3, %5, %1;\n\t}"                                \
             : "+r"(v), "+r"(k), "+r"(base) : "r"(c), "r"(one), "r"(0u - one));                                     \
     }
-    OBF_KTH_STEP(16, 0xFFFFu)
-    OBF_KTH_STEP(8, 0xFFu)
-    OBF_KTH_STEP(4, 0xFu)
-    OBF_KTH_STEP(2, 0x3u)
+    OBF_KTH_STEP(16)
+    OBF_KTH_STEP(8)
+    OBF_KTH_STEP(4)
+    OBF_KTH_STEP(2)
 #undef OBF_KTH_STEP
     return base + ((k >= (int)(v & 1u)) ? 1 : 0);
 }
