@@ -121,7 +121,7 @@ typedef struct {
     int32_t  n_rand_white;
     const float *weights;         /* DEVICE float[4][10]; required for OTHELLO_POLICY_GREEDY */
     int32_t  t_max;               /* trajectory capacity in plies (120 holds every game from <= 60 empties) */
-    int64_t  stride;              /* games per trajectory row (>= n_games) */
+    int64_t  stride;              /* games per trajectory row (>= n_games); random engine: (t_max + 2) * stride < 2^32 */
     uint64_t *traj_black;         /* [t_max+1][stride] position before ply t (recorder.add, game_runner.py:170,159); NULL = none */
     uint64_t *traj_white;
     uint8_t  *traj_move;          /* [t_max][stride] move played at ply t (0..63, 64 = pass) */

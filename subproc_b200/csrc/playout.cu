@@ -22,24 +22,26 @@ namespace {
 // the random engine (uniform over puttables()); the greedy engine lives in greedy.cu
 struct Game {
     u64 own, opp;
-    u64 *tb, *tw;
-    uint8_t *tm;
+    unsigned off;               // element index t * stride + game into the three trajectory arrays
     int t;
 };
 
 // One ply.  BLACK: 1 = Black moves, 0 = White moves (known at compile time when every game of the
 // launch starts with the same colour: Black and White then alternate strictly, passes included),
 // -1 = read `black_moves`.  Returns false when the game is over.
-// TRAJ: 0 = no trajectory, 1 = trajectory with capacity checks, 2 = trajectory that is known to fit (standard
+// TRAJ: 0 = no trajectory; 1 = trajectory with capacity checks; 2 = a trajectory that is known to fit (standard
 // opening and t_max >= 120: 60 moves + at most 60 interleaved passes), so the two checks per ply fall away.
+// The three trajectory arrays are addressed with ONE 32-bit element index t * stride + game (a 32-bit add per
+// ply instead of three 64-bit pointer increments), hence (t_max + 2) * stride < 2^32 (othello_playout checks).
 template <int TRAJ, int BLACK>
-__device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int t_max, int64_t stride, const Rays &rays)
+__device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int t_max, int64_t stride, const Rays &rays,
+                                         u64 *__restrict__ traj_black = nullptr, u64 *__restrict__ traj_white = nullptr,
+                                         uint8_t *__restrict__ traj_move = nullptr)
 {
     const bool bm = BLACK < 0 ? black_moves : (BLACK == 1);
     if (TRAJ == 2 || (TRAJ == 1 && g.t <= t_max)) {
-        __stcs(g.tb, bm ? g.own : g.opp);
-        __stcs(g.tw, bm ? g.opp : g.own);
-        g.tb += stride; g.tw += stride;
+        __stcs(traj_black + g.off, bm ? g.own : g.opp);
+        __stcs(traj_white + g.off, bm ? g.opp : g.own);
     }
     const u64 own_r = obf::rev64(g.own), opp_r = obf::rev64(g.opp);
     const u64 legal = obf::legal_moves(g.own, g.opp, own_r, opp_r);
@@ -57,7 +59,8 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         x = rays(obf::kRayDirs, move);
         f = obf::flips_for<true>(move, g.own, g.opp, own_r, opp_r, rays);
     }
-    if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) { __stcs(g.tm, (uint8_t)move); g.tm += stride; }
+    if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) __stcs(traj_move + g.off, (uint8_t)move);
+    if (TRAJ) g.off += (unsigned)stride;
     // put_s: place, flip, nturn += 1, turn toggles (board.py:203-208)
     const u64 moved = g.own | f | x;
     g.own = g.opp & ~f;
@@ -84,21 +87,19 @@ __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_pla
         bool black_moves = UNIFORM ? true : (a.turn0[gi] == OTHELLO_BLACK);
         Game g;
         g.own = black_moves ? b0 : w0; g.opp = black_moves ? w0 : b0;
-        g.tb = TRAJ ? (u64 *)a.traj_black + gi : nullptr;
-        g.tw = TRAJ ? (u64 *)a.traj_white + gi : nullptr;
-        g.tm = TRAJ ? a.traj_move + gi : nullptr;
         g.t = 0;
+        g.off = (unsigned)gi;
         const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
         const int t_max = a.t_max;
         const int64_t stride = a.stride;
 
         if (UNIFORM) {
             for (;;) {
-                if (!play_ply<TRAJ, 1>(g, true, key, t_max, stride, rays)) { black_moves = true; break; }
-                if (!play_ply<TRAJ, 0>(g, false, key, t_max, stride, rays)) { black_moves = false; break; }
+                if (!play_ply<TRAJ, 1>(g, true, key, t_max, stride, rays, (u64 *)a.traj_black, (u64 *)a.traj_white, a.traj_move)) { black_moves = true; break; }
+                if (!play_ply<TRAJ, 0>(g, false, key, t_max, stride, rays, (u64 *)a.traj_black, (u64 *)a.traj_white, a.traj_move)) { black_moves = false; break; }
             }
         } else {
-            while (play_ply<TRAJ, -1>(g, black_moves, key, t_max, stride, rays)) black_moves = !black_moves;
+            while (play_ply<TRAJ, -1>(g, black_moves, key, t_max, stride, rays, (u64 *)a.traj_black, (u64 *)a.traj_white, a.traj_move)) black_moves = !black_moves;
         }
         const u64 fb = black_moves ? g.own : g.opp, fw = black_moves ? g.opp : g.own;
         a.nplies[gi] = g.t;
@@ -115,7 +116,8 @@ int launch(const othello_playout_args &a, cudaStream_t s)
 {
     const unsigned blocks = ob_blocks(a.n_games, kThreads);
     if (a.traj_black) {
-        const bool fits = a.black0 == nullptr && a.t_max >= 120;          // every game from the standard opening fits
+        if ((int64_t)(a.t_max + 2) * a.stride >= (1ll << 32)) return OTHELLO_E_INVALID;   // 32-bit trajectory index
+        const bool fits = a.black0 == nullptr && a.t_max >= 120;             // every game from the standard opening fits
         if (a.turn0) {
             if (fits) playout_kernel<2, false><<<blocks, kThreads, 0, s>>>(a);
             else playout_kernel<1, false><<<blocks, kThreads, 0, s>>>(a);
