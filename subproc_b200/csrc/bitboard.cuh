@@ -99,6 +99,8 @@ __device__ __forceinline__ float eval_linear(u64 own, u64 opp, const float *__re
 struct Rays {
     const u64 *t;
     __device__ __forceinline__ u64 operator()(int d, int s) const { return t[d * 64 + s]; }
+    __device__ __forceinline__ u64 word(u32 i) const { return t[i]; }
+    __device__ __forceinline__ u32 byte(u32 i) const { return ((const uint8_t *)t)[i]; }
 };
 
 // the table is built at compile time and lives in global memory (L2-resident); a CTA copies its 2 KB
@@ -107,7 +109,7 @@ struct RayTableInit {
     u64 v[obf::kRayTable64];
     constexpr RayTableInit() : v()
     {
-        for (int i = 0; i < obf::kRayTable64; i++) v[i] = obf::make_ray(i >> 6, i & 63);
+        for (int i = 0; i < obf::kRayTable64; i++) v[i] = obf::make_table_word(i);
     }
 };
 static __device__ const RayTableInit kRayTable = RayTableInit();

@@ -111,12 +111,13 @@ template <int D> OBF_HD Inter ishift2(Inter v)       // 2 * D squares up
 }
 
 // Flood to the LEFT (towards higher squares) by D: squares just beyond a run of `m` discs that
-// starts right after an `own` disc.  Kogge-Stone: 1 + 1 + 2 + 2 = up to 6 discs.
-template <int D> OBF_HD Inter flood_up(Inter own, Inter m)
+// starts right after an `own` disc.  Kogge-Stone: 1 + 1 + 2 + 2 = up to 6 discs.  p = pairs(m): discs of m
+// whose neighbour D squares down is in m as well.
+template <int D> OBF_HD Inter pairs(Inter m) { return iand(m, ishift<D>(m)); }
+template <int D> OBF_HD Inter flood_up(Inter own, Inter m, Inter p)
 {
     Inter f = iand(m, ishift<D>(own));
     f = ior(f, iand(m, ishift<D>(f)));
-    const Inter p = iand(m, ishift<D>(m));
     f = ior(f, iand(p, ishift2<D>(f)));
     f = ior(f, iand(p, ishift2<D>(f)));
     return ishift<D>(f);
@@ -131,13 +132,24 @@ OBF_HD u32 row_up32(u32 own, u32 m)
     return (m + a) & ~m;                // carry-out squares (bits set by the add that were clear in m)
 }
 
+// the pair masks of the three flood directions
+struct Pairs { Inter p8, p7, p9; };
+OBF_HD Pairs make_pairs(Inter opp, Inter m) { return Pairs{pairs<8>(opp), pairs<7>(m), pairs<9>(m)}; }
+// ... of the board rotated by 180 degrees, from those of the board as it stands: a pair (s - D, s) is the pair
+// (63 - s, 63 - s + D) of the rotated board, so the rotated mask is the rotation shifted up by D -- two BREVs
+// (XU pipe) instead of two LOP3 (the saturated ALU pipe) per direction
+OBF_HD Pairs rotated_pairs(const Pairs &q)
+{
+    return Pairs{ishift<8>(rev_inter(q.p8)), ishift<7>(rev_inter(q.p7)), ishift<9>(rev_inter(q.p9))};
+}
+
 // the four "up" directions (+1, +7, +8, +9) of one board; m = opp without the a/h files
-OBF_HD Inter moves_up(Inter own, Inter opp, Inter m)
+OBF_HD Inter moves_up(Inter own, Inter opp, Inter m, const Pairs &q)
 {
     Inter r = Inter{row_up32(own.a, m.a), row_up32(own.b, m.b)};
-    r = ior(r, flood_up<8>(own, opp));
-    r = ior(r, flood_up<7>(own, m));
-    r = ior(r, flood_up<9>(own, m));
+    r = ior(r, flood_up<8>(own, opp, q.p8));
+    r = ior(r, flood_up<7>(own, m, q.p7));
+    r = ior(r, flood_up<9>(own, m, q.p9));
     return r;
 }
 
@@ -158,8 +170,10 @@ OBF_HD Inter legal_inter(const Pos4 &q)
 {
     // kInner32 is a palindrome, so the rotated inner mask is the same constant
     const Inter m = Inter{q.p.a & kInner32, q.p.b & kInner32}, mr = Inter{q.rp.a & kInner32, q.rp.b & kInner32};
-    const Inter up = moves_up(q.o, q.p, m);
-    const Inter down = moves_up(q.ro, q.rp, mr);                              // the rotated board
+    const Pairs pu = make_pairs(q.p, m);
+    const Pairs pd = rotated_pairs(pu);                                       // BREV (XU pipe) instead of LOP3 (ALU pipe)
+    const Inter up = moves_up(q.o, q.p, m, pu);
+    const Inter down = moves_up(q.ro, q.rp, mr, pd);                          // the rotated board
     return iand(ior(up, rev_inter(down)), Inter{~(q.o.a | q.p.a), ~(q.o.b | q.p.b)});
 }
 
@@ -201,9 +215,14 @@ OBF_HD void mobility_both(u64 black, u64 white, int &mob_black, int &mob_white)
 OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp); }
 
 // ---- put(): flips through carry propagation along rays -----------------------------------------
-// ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge
+// ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge; behind the
+// four ray rows: a row of single-square masks, and the tables of the rank look-up (row_flips below)
 constexpr int kRayDirs = 4;
-constexpr int kRayTable64 = (kRayDirs + 1) * 64;   // table entries: the four ray rows + a row of single-square masks
+constexpr int kRankMul64 = (kRayDirs + 1) * 64;        // [8]: 1 << 8 * rank
+constexpr int kRowOutflank64 = kRankMul64 + 8;         // bytes [file][opp rank & 0x7e] (odd entries unused)
+constexpr int kRowFlip64 = kRowOutflank64 + 8 * 128 / 8;   // bytes [file][outflanking own discs]
+constexpr int kKthBit64 = kRowFlip64 + 8 * 256 / 8;    // bytes [byte value][k]: position of the k-th set bit of a byte
+constexpr int kRayTable64 = kKthBit64 + 256 * 8 / 8;   // table entries (u64)
 OBF_HD constexpr u64 make_ray(int d, int s)
 {
     if (d == kRayDirs) return 1ull << s;                               // row 4: the square itself (1 << s as a table load)
@@ -213,6 +232,74 @@ OBF_HD constexpr u64 make_ray(int d, int s)
     int x = (s & 7) + dx, y = (s >> 3) + dy;
     while (x >= 0 && x < 8 && y < 8) { r |= 1ull << (x + 8 * y); x += dx; y += dy; }
     return r;
+}
+// A move on file x of a rank whose opponent discs are `opp` (8 bits): the squares on which an own disc would
+// close a run of opponent discs that starts next to x (at most one on either side).
+OBF_HD constexpr u32 row_outflank(int x, u32 opp)
+{
+    u32 r = 0;
+    int i = x + 1;
+    while (i <= 6 && ((opp >> i) & 1u)) i++;
+    if (i > x + 1) r |= 1u << i;
+    i = x - 1;
+    while (i >= 1 && ((opp >> i) & 1u)) i--;
+    if (i < x - 1) r |= 1u << i;
+    return r;
+}
+// ... and the discs flipped when own discs stand on `closing` of those squares: everything between x and the
+// nearest closing disc on either side.
+OBF_HD constexpr u32 row_flipped(int x, u32 closing)
+{
+    u32 r = 0;
+    for (int i = x + 1; i < 8; i++)
+        if ((closing >> i) & 1u) { r |= ((1u << i) - 1u) & ~((2u << x) - 1u); break; }
+    for (int i = x - 1; i >= 0; i--)
+        if ((closing >> i) & 1u) { r |= ((1u << x) - 1u) & ~((2u << i) - 1u); break; }
+    return r;
+}
+// position of the k-th (0-based, ascending) set bit of an 8-bit value (0 if it has fewer)
+OBF_HD constexpr u32 kth_bit_of_byte(u32 v, int k)
+{
+    for (int i = 0; i < 8; i++)
+        if ((v >> i) & 1u) { if (k == 0) return (u32)i; k--; }
+    return 0;
+}
+// word i of the whole table
+OBF_HD constexpr u64 make_table_word(int i)
+{
+    if (i < kRankMul64) return make_ray(i >> 6, i & 63);
+    if (i < kRowOutflank64) return 1ull << (8 * (i - kRankMul64));
+    u64 w = 0;
+    for (int j = 0; j < 8; j++) {
+        if (i >= kKthBit64) {
+            w |= (u64)kth_bit_of_byte((u32)(i - kKthBit64), j) << (8 * j);
+        } else if (i < kRowFlip64) {
+            const int e = (i - kRowOutflank64) * 8 + j;
+            w |= (u64)row_outflank(e >> 7, (u32)(e & 0x7e)) << (8 * j);
+        } else {
+            const int e = (i - kRowFlip64) * 8 + j;
+            w |= (u64)row_flipped(e >> 8, (u32)(e & 0xff)) << (8 * j);
+        }
+    }
+    return w;
+}
+
+// The two horizontal rays of a move by table look-up instead of two carry chains: the rank of the move is a BYTE
+// of the bitboards, so extracting it is one PRMT per colour; [file][opponent discs] gives the squares where an own
+// disc would outflank, [file][those that are own] the flipped discs, which a multiply puts back on the rank.  6
+// ALU-pipe instructions instead of 16 + 2 POPC; the look-ups run on the LSU pipe, idle in the playout kernel.
+// rays.byte(i) = byte i of the table, rays.word(i) = word i.
+template <typename RayTable>
+OBF_HD void row_flips(int s, u64 own, u64 opp, const RayTable &rays, u32 &f_lo, u32 &f_hi)
+{
+    const u32 y = (u32)s >> 3, x = (u32)s & 7u;
+    const u32 ob = byte_perm(lo32(own), hi32(own), y);       // byte 0 = the rank of the move (bytes 1..3: the first rank)
+    const u32 pb = byte_perm(lo32(opp), hi32(opp), y);
+    const u32 cand = rays.byte(kRowOutflank64 * 8 + x * 128 + (pb & 0x7eu));
+    const u32 flip = rays.byte(kRowFlip64 * 8 + x * 256 + (cand & ob));
+    const u64 mul = rays.word(kRankMul64 + y);
+    f_lo += flip * lo32(mul);
+    f_hi += flip * hi32(mul);
 }
 
 // one ray: x = move bit, R = ray mask beyond it.  Returns the opponent run that an own disc closes.
@@ -247,7 +334,8 @@ __device__ __forceinline__ void ray_accumulate(u32 &acc_lo, u32 &acc_hi, u64 x, 
 // index of the k-th (0-based, ascending) set bit of a non-empty mask, k < popc(mask): puttables()[k]
 // (board.py:48-51).  Binary search on POPC (XU pipe); the conditional updates of k and of the bit
 // base are predicated IMADs (FMA pipe), so a step costs the ALU pipe three instructions.
-__device__ __forceinline__ int kth_set_bit(u64 mask, int k)
+template <bool BYTE_LUT, typename RayTable>
+__device__ __forceinline__ int kth_set_bit(u64 mask, int k, const RayTable &rays)
 {
     const u32 one = kOpaqueOne;
     u32 v = lo32(mask);
@@ -269,18 +357,26 @@ __device__ __forceinline__ int kth_set_bit(u64 mask, int k)
     }
     OBF_KTH_STEP(16)
     OBF_KTH_STEP(8)
+    if (BYTE_LUT) {
+        // the byte that holds the bit is the low byte of the window: its k-th set bit from [byte][k] (one LDS instead
+        // of three more rounds of POPC + compare + shift)
+        return base + (int)rays.byte(kKthBit64 * 8 + (v & 0xffu) * 8 + (u32)k);
+    }
     OBF_KTH_STEP(4)
     OBF_KTH_STEP(2)
 #undef OBF_KTH_STEP
     return base + ((k >= (int)(v & 1u)) ? 1 : 0);
 }
+struct NoTable { __device__ __forceinline__ u32 byte(u32) const { return 0; } };
+__device__ __forceinline__ int kth_set_bit(u64 mask, int k) { return kth_set_bit<false>(mask, k, NoTable()); }
 #endif
 
 // Discs flipped by an `own` disc on the EMPTY square s (board.py:161-174); rays = table [4][64].
 // BIT_LUT: take the move bit and its rotation from the table's fifth row (two LDS) instead of a variable
 // 64-bit shift (two ALU instructions) + two BREVs.  Pays in the random playout kernel, whose LSU pipe idles
 // (+1.1 %); costs the greedy kernel 0.8 % (its LSU pipe also carries the work-item lists), so it is a choice.
-template <bool BIT_LUT = false, typename RayTable>
+// ROW_LUT: the two horizontal rays through row_flips.
+template <bool BIT_LUT = false, bool ROW_LUT = false, typename RayTable>
 OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTable &rays)
 {
     const int sr = 63 - s;
@@ -289,8 +385,9 @@ OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTab
     const u64 xr = BIT_LUT ? rays(kRayDirs, sr) : rev64(x);   // (two BREVs on the XU pipe, not two more ALU shifts)
     const u32 one = kOpaqueOne;
     u32 f_lo = 0, f_hi = 0, r_lo = 0, r_hi = 0;
+    if (ROW_LUT) row_flips(s, own, opp, rays, f_lo, f_hi);
 #pragma unroll
-    for (int d = 0; d < kRayDirs; d++) {
+    for (int d = ROW_LUT ? 1 : 0; d < kRayDirs; d++) {
         ray_accumulate(f_lo, f_hi, x, rays(d, s), own, opp, one);
         ray_accumulate(r_lo, r_hi, xr, rays(d, sr), own_r, opp_r, one);
     }
@@ -298,7 +395,12 @@ OBF_HD u64 flips_for(int s, u64 own, u64 opp, u64 own_r, u64 opp_r, const RayTab
 #else
     const u64 x = 1ull << s, xr = 1ull << sr;
     u64 f = 0, fr = 0;
-    for (int d = 0; d < kRayDirs; d++) {
+    if (ROW_LUT) {
+        u32 f_lo = 0, f_hi = 0;
+        row_flips(s, own, opp, rays, f_lo, f_hi);
+        f = pack(f_lo, f_hi);
+    }
+    for (int d = ROW_LUT ? 1 : 0; d < kRayDirs; d++) {
         f |= ray_flips(x, rays(d, s), own, opp);
         fr |= ray_flips(xr, rays(d, sr), own_r, opp_r);
     }

@@ -20,6 +20,7 @@ using namespace obp;
 
 namespace {
 
+constexpr bool kRowLut = true;               // horizontal rays of a flip from the rank tables (+3 % on B200)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxItems = 32 * 60;            // 32 games x at most 60 empty squares: holds ANY pair of bitboards, not only
                                               // positions reachable from the opening (<= 33 legal moves)
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                     const unsigned it = ws.item[j];
                     owner = (it >> 8) & 31u; sq = it & 63u;
                     const u64 o = ws.own[owner], p = ws.opp[owner];
-                    const u64 f = obf::flips_for((int)sq, o, p, obf::rev64(o), obf::rev64(p), rays);
+                    const u64 f = obf::flips_for<false, kRowLut>((int)sq, o, p, obf::rev64(o), obf::rev64(p), rays);
                     kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, (it & 0x8000u) ? w_s + kW : w_s));
                     before = ws.best_key[owner];
                 }
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                 else if (random_now) move = obf::kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
                 else move = __ffsll((long long)legal) - 1;
                 x = 1ull << move;
-                f = obf::flips_for(move, own, opp, own_r, opp_r, rays);
+                f = obf::flips_for<false, kRowLut>(move, own, opp, own_r, opp_r, rays);
             }
             if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
             const u64 moved = own | f | x;                    // put_s (board.py:203-208)

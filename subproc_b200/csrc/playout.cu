@@ -19,6 +19,12 @@ using namespace obp;
 
 namespace {
 
+// Table look-ups on the idle LSU pipe instead of ALU-pipe instructions (A/B on B200, profiles/playout_variants_r02.txt):
+// the two horizontal rays of a flip from the rank tables (+3.8 %), the last three rounds of the k-th-set-bit search
+// from the byte table (+2.3 %)
+constexpr bool kRowLut = true;
+constexpr bool kKthLut = true;
+
 // the random engine (uniform over puttables()); the greedy engine lives in greedy.cu
 struct Game {
     u64 own, opp;
@@ -55,9 +61,9 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
         // random one; behind a random engine both draw the same k-th move from stream 1, so the
         // budgets n_rand_* do not change any game played by this kernel.
-        move = obf::kth_set_bit(legal, (int)rng_below(r1, (u32)n));
+        move = obf::kth_set_bit<kKthLut>(legal, (int)rng_below(r1, (u32)n), rays);
         x = rays(obf::kRayDirs, move);
-        f = obf::flips_for<true>(move, g.own, g.opp, own_r, opp_r, rays);
+        f = obf::flips_for<true, kRowLut>(move, g.own, g.opp, own_r, opp_r, rays);
     }
     if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) __stcs(traj_move + g.off, (uint8_t)move);
     if (TRAJ) g.off += (unsigned)stride;

@@ -57,6 +57,8 @@ def test_fast_legal_and_flips_match_oracle(fb, oracle):
         fb.fb_flips(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
         _, _, want, _ = oracle.put(b, w, piece, sq)
         assert np.array_equal(out, want)
+        fb.fb_flips_rowlut(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))      # horizontal rays by rank look-up
+        assert np.array_equal(out, want)
 
 
 def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
@@ -70,6 +72,8 @@ def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
     assert np.array_equal(out, oracle.puttables(own, opp, 1))
     fb.fb_flips(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
     _, _, want, ret = oracle.put(own, opp, 1, sq)
+    assert np.array_equal(out, want)
+    fb.fb_flips_rowlut(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
     assert np.array_equal(out, want)
     assert (ret >= 6).sum() > 50 and (ret == 0).sum() > 1000          # six-disc runs and dead rays are both present
 
@@ -108,3 +112,40 @@ def test_child_mobility_from_the_prepared_parent(fb, oracle):
         after = oracle.puttables(nb, nw, piece)
         want = np.array([bin(int(v)).count("1") if f else -1 for v, f in zip(after, flips)], dtype=np.int32)
         assert np.array_equal(got, want)
+
+
+def test_rank_tables_every_rank_file_and_pattern(fb, oracle):
+    """the rank look-up of the horizontal rays (obf::row_flips): every rank, every file, all 3^7 fillings of the other
+    seven squares of the rank, other ranks filled at random (they must not matter to the two horizontal rays, and the
+    remaining six rays still go through the carry chains)"""
+    rng = np.random.RandomState(7)
+    pats = np.array(np.meshgrid(*[[0, 1, 2]] * 7, indexing='ij')).reshape(7, -1).T       # 2187 x 7
+    own_l, opp_l, sq_l = [], [], []
+    for y in range(8):
+        for x in range(8):
+            cols = [c for c in range(8) if c != x]
+            o = np.zeros(len(pats), dtype=np.uint64)
+            p = np.zeros(len(pats), dtype=np.uint64)
+            for j, c in enumerate(cols):
+                o |= (pats[:, j] == 1).astype(np.uint64) << np.uint64(8 * y + c)
+                p |= (pats[:, j] == 2).astype(np.uint64) << np.uint64(8 * y + c)
+            noise_occ = rng.randint(0, 2 ** 62, size=len(pats)).astype(np.uint64) << np.uint64(2)
+            noise_col = rng.randint(0, 2 ** 62, size=len(pats)).astype(np.uint64) << np.uint64(2)
+            keep = ~(np.uint64(0xff) << np.uint64(8 * y))
+            own_l.append(o | (noise_occ & noise_col & keep))
+            opp_l.append(p | (noise_occ & ~noise_col & keep))
+            sq_l.append(np.full(len(pats), 8 * y + x, dtype=np.uint8))
+    own = np.ascontiguousarray(np.concatenate(own_l)); opp = np.ascontiguousarray(np.concatenate(opp_l))
+    sq = np.ascontiguousarray(np.concatenate(sq_l))
+    out = np.zeros(own.size, dtype=np.uint64)
+    fb.fb_flips_rowlut(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))
+    _, _, want, _ = oracle.put(own, opp, 1, sq)
+    assert own.size == 64 * 2187 and np.array_equal(out, want)
+
+
+def test_kth_set_bit_table(fb):
+    """[byte][k] -> position of the k-th set bit (the last step of obf::kth_set_bit in the playout kernel)"""
+    for v in range(256):
+        bits = [i for i in range(8) if (v >> i) & 1]
+        for k, want in enumerate(bits):
+            assert fb.fb_kth_table(v, k) == want
