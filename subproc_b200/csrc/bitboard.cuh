@@ -114,9 +114,12 @@ struct RayTableInit {
 };
 static __device__ const RayTableInit kRayTable = RayTableInit();
 
+// N = obf::kRayBasic64: the ray masks of the carry-chain put() (2.5 KB); obf::kRayTable64: + the line look-up
+// tables of the game kernels (11.9 KB)
+template <int N = obf::kRayBasic64>
 __device__ __forceinline__ void fill_rays(u64 *t)
 {
-    for (int i = threadIdx.x; i < obf::kRayTable64; i += blockDim.x) t[i] = kRayTable.v[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) t[i] = kRayTable.v[i];
 }
 
 // Board.put(piece, x, y) (board.py:161-174): flips of an own disc on EMPTY square s

@@ -211,18 +211,21 @@ OBF_HD void mobility_both(u64 black, u64 white, int &mob_black, int &mob_white)
     mob_white = popc_inter(legal_inter(swapped(q)));
 }
 
-// (own_r / opp_r = rev64(own / opp) are what flips_for needs; move generation rotates in its own layout)
-OBF_HD u64 legal_moves(u64 own, u64 opp, u64, u64) { return legal_moves(own, opp); }
 
 // ---- put(): flips through carry propagation along rays -----------------------------------------
 // ray table: ray[d][s] = squares strictly beyond s in direction d in {+1, +7, +8, +9}, up to the edge; behind the
 // four ray rows: a row of single-square masks, and the tables of the rank look-up (row_flips below)
 constexpr int kRayDirs = 4;
-constexpr int kRankMul64 = (kRayDirs + 1) * 64;        // [8]: 1 << 8 * rank
-constexpr int kRowOutflank64 = kRankMul64 + 8;         // bytes [file][opp rank & 0x7e] (odd entries unused)
-constexpr int kRowFlip64 = kRowOutflank64 + 8 * 128 / 8;   // bytes [file][outflanking own discs]
+constexpr int kRayBasic64 = (kRayDirs + 1) * 64;       // what the carry-chain form of put() needs: rays + single squares
+constexpr int kRankMul64 = kRayBasic64;                // [8]: 1 << 8 * rank
+constexpr int kFileMul64 = kRankMul64 + 8;             // [8]: low word 1 << (7 - file), high word 1 << file
+constexpr int kDiag9_64 = kFileMul64 + 8;              // [64]: the whole +9 / -9 diagonal through a square
+constexpr int kDiag7_64 = kDiag9_64 + 64;              // [64]: the whole +7 / -7 diagonal
+constexpr int kRowOutflank64 = kDiag7_64 + 64;         // bytes [position on the line][opponent discs of the line]
+constexpr int kRowFlip64 = kRowOutflank64 + 8 * 256 / 8;   // bytes [position on the line][outflanking own discs]
 constexpr int kKthBit64 = kRowFlip64 + 8 * 256 / 8;    // bytes [byte value][k]: position of the k-th set bit of a byte
-constexpr int kRayTable64 = kKthBit64 + 256 * 8 / 8;   // table entries (u64)
+constexpr int kSpread64 = kKthBit64 + 256 * 8 / 8;     // [256]: bit k of the index on bit 8 * k (a file-a column)
+constexpr int kRayTable64 = kSpread64 + 256;           // table entries (u64): 11.9 KB
 OBF_HD constexpr u64 make_ray(int d, int s)
 {
     if (d == kRayDirs) return 1ull << s;                               // row 4: the square itself (1 << s as a table load)
@@ -264,18 +267,34 @@ OBF_HD constexpr u32 kth_bit_of_byte(u32 v, int k)
         if ((v >> i) & 1u) { if (k == 0) return (u32)i; k--; }
     return 0;
 }
+// every square of the diagonal through s (s included), step 9 or 7
+OBF_HD constexpr u64 make_diagonal(int step, int s)
+{
+    const int dx = step == 9 ? 1 : -1;
+    u64 r = 0;
+    for (int k = -7; k <= 7; k++) {
+        const int x = (s & 7) + k * dx, y = (s >> 3) + k;
+        if (x >= 0 && x < 8 && y >= 0 && y < 8) r |= 1ull << (x + 8 * y);
+    }
+    return r;
+}
 // word i of the whole table
 OBF_HD constexpr u64 make_table_word(int i)
 {
     if (i < kRankMul64) return make_ray(i >> 6, i & 63);
-    if (i < kRowOutflank64) return 1ull << (8 * (i - kRankMul64));
+    if (i < kFileMul64) return 1ull << (8 * (i - kRankMul64));
+    if (i < kDiag9_64) return ((1ull << (i - kFileMul64)) << 32) | (1ull << (7 - (i - kFileMul64)));
+    if (i < kDiag7_64) return make_diagonal(9, i - kDiag9_64);
+    if (i < kRowOutflank64) return make_diagonal(7, i - kDiag7_64);
     u64 w = 0;
     for (int j = 0; j < 8; j++) {
-        if (i >= kKthBit64) {
+        if (i >= kSpread64) {
+            w |= (u64)(((i - kSpread64) >> j) & 1) << (8 * j);
+        } else if (i >= kKthBit64) {
             w |= (u64)kth_bit_of_byte((u32)(i - kKthBit64), j) << (8 * j);
         } else if (i < kRowFlip64) {
             const int e = (i - kRowOutflank64) * 8 + j;
-            w |= (u64)row_outflank(e >> 7, (u32)(e & 0x7e)) << (8 * j);
+            w |= (u64)row_outflank(e >> 8, (u32)(e & 0xff)) << (8 * j);
         } else {
             const int e = (i - kRowFlip64) * 8 + j;
             w |= (u64)row_flipped(e >> 8, (u32)(e & 0xff)) << (8 * j);
@@ -295,7 +314,7 @@ OBF_HD void row_flips(int s, u64 own, u64 opp, const RayTable &rays, u32 &f_lo, 
     const u32 y = (u32)s >> 3, x = (u32)s & 7u;
     const u32 ob = byte_perm(lo32(own), hi32(own), y);       // byte 0 = the rank of the move (bytes 1..3: the first rank)
     const u32 pb = byte_perm(lo32(opp), hi32(opp), y);
-    const u32 cand = rays.byte(kRowOutflank64 * 8 + x * 128 + (pb & 0x7eu));
+    const u32 cand = rays.byte(kRowOutflank64 * 8 + x * 256 + (pb & 0xffu));
     const u32 flip = rays.byte(kRowFlip64 * 8 + x * 256 + (cand & ob));
     const u64 mul = rays.word(kRankMul64 + y);
     f_lo += flip * lo32(mul);
@@ -370,6 +389,71 @@ __device__ __forceinline__ int kth_set_bit(u64 mask, int k, const RayTable &rays
 struct NoTable { __device__ __forceinline__ u32 byte(u32) const { return 0; } };
 __device__ __forceinline__ int kth_set_bit(u64 mask, int k) { return kth_set_bit<false>(mask, k, NoTable()); }
 #endif
+
+OBF_HD u32 umulhi32(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+
+// put() entirely by table look-up: the FOUR lines through the move (rank, file, two diagonals) instead of eight rays.
+// Each line is gathered into a byte per colour, [position][opponent byte] gives the squares where an own disc would
+// outflank, [position][those that are own] the flipped discs of the line, which are scattered back.  What makes this
+// pay on a 32-bit machine whose ALU pipe is the bottleneck is that gather and scatter are multiplies (FMA pipe):
+//   rank      the byte itself (PRMT); scatter = multiply by 1 << 8 * rank
+//   file      multiply by 1 << (7 - file) moves the file onto bit 7 of every byte (no other bit lands there), the
+//             high half of a multiply by 2^25 + 2^18 + 2^11 + 2^4 collects the four bits of a word (all 16 partial
+//             products fall on different bits, so nothing carries); scatter = [byte] -> file-a column, times 1 << file
+//   diagonal  a diagonal has one square per file: mask it, OR the two words, multiply by 0x01010101 -- the top byte is
+//             the OR of the four bytes, bit j = file j; scatter = the byte times 0x01010101, masked with the diagonal
+// and a byte with junk above it needs no cleaning where it is ANDed with a clean table byte.  27 ALU-pipe
+// instructions for a move instead of 52, no rotated board, no POPC.  `one` = kOpaqueOne on the device (keeps the
+// shifts and address additions on the FMA pipe), 1 on the host.
+template <typename RayTable>
+OBF_HD u64 flips_lut(int s, u64 own, u64 opp, const RayTable &T, u32 one)
+{
+    const u32 y = (u32)s >> 3, x = (u32)s & 7u;
+    const u32 olo = lo32(own), ohi = hi32(own), plo = lo32(opp), phi = hi32(opp);
+    const u32 t1x = kRowOutflank64 * 8 + x * 256, t2x = kRowFlip64 * 8 + x * 256;      // tables of position x
+    const u32 t1y = kRowOutflank64 * 8 + y * 256, t2y = kRowFlip64 * 8 + y * 256;
+    const u32 shr24 = one << 8;                                  // v >> 24 == umulhi(v, 1 << 8)
+    u32 f_lo, f_hi;
+    {   // the rank
+        const u32 ob = byte_perm(olo, ohi, y);                   // byte 0 = the rank (bytes 1..3: junk)
+        const u32 pb = byte_perm(plo, phi, y) & 0xffu;
+        const u32 flip = T.byte((T.byte(pb * one + t1x) & ob) * one + t2x);
+        const u64 mul = T.word(kRankMul64 + y);
+        f_lo = flip * lo32(mul);
+        f_hi = flip * hi32(mul);
+    }
+    {   // the file
+        const u64 fm = T.word(kFileMul64 + x);
+        const u32 up = lo32(fm);
+        const u32 kLo = 0x02040810u, kHi = 0x20408100u;          // bits 8k+7 -> bit k / bit 4+k of the high half
+        const u32 pb = (umulhi32((plo * up) & 0x80808080u, kLo) + umulhi32((phi * up) & 0x80808080u, kHi)) & 0xffu;
+        const u32 ob = umulhi32((olo * up) & 0x80808080u, kLo) + umulhi32((ohi * up) & 0x80808080u, kHi);   // (junk above bit 7)
+        const u32 flip = T.byte((T.byte(pb * one + t1y) & ob) * one + t2y);
+        const u64 col = T.word(kSpread64 + flip);
+        f_lo += lo32(col) * hi32(fm);
+        f_hi += hi32(col) * hi32(fm);
+    }
+#define OBF_DIAGONAL(TABLE)                                                                                        \
+    {                                                                                                              \
+        const u64 d = T.word((TABLE) + (u32)s);                                                                    \
+        const u32 pb = umulhi32(((plo & lo32(d)) | (phi & hi32(d))) * 0x01010101u, shr24);                         \
+        const u32 ob = umulhi32(((olo & lo32(d)) | (ohi & hi32(d))) * 0x01010101u, shr24);                         \
+        const u32 r = T.byte((T.byte(pb * one + t1x) & ob) * one + t2x) * 0x01010101u;                            \
+        f_lo |= r & lo32(d);                                                                                       \
+        f_hi |= r & hi32(d);                                                                                       \
+    }
+    OBF_DIAGONAL(kDiag9_64)
+    OBF_DIAGONAL(kDiag7_64)
+#undef OBF_DIAGONAL
+    return pack(f_lo, f_hi);
+}
 
 // Discs flipped by an `own` disc on the EMPTY square s (board.py:161-174); rays = table [4][64].
 // BIT_LUT: take the move bit and its rotation from the table's fifth row (two LDS) instead of a variable

@@ -20,7 +20,6 @@ using namespace obp;
 
 namespace {
 
-constexpr bool kRowLut = true;               // horizontal rays of a flip from the rank tables (+3 % on B200)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxItems = 32 * 60;            // 32 games x at most 60 empty squares: holds ANY pair of bitboards, not only
                                               // positions reachable from the opening (<= 33 legal moves)
@@ -55,7 +54,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     // which colours are served by the greedy engine (the other answers uniformly at random)
     const bool greedy_b = a.policy == OTHELLO_POLICY_GREEDY;
     const bool greedy_w = (a.policy_white == -1 ? a.policy : a.policy_white) == OTHELLO_POLICY_GREEDY;
-    fill_rays(ray_s);
+    fill_rays<obf::kRayTable64>(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
     WarpScratch &ws = scratch[threadIdx.x >> 5];
@@ -85,16 +84,15 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
     const bool live = !done;
     int plies = 0, n_black = 0, n_white = 0;               // the game's result, for the launch totals
     while (__any_sync(kFull, !done)) {
-        u64 legal = 0, own_r = 0, opp_r = 0;
+        u64 legal = 0;
         if (!done) {
             if (TRAJ && t <= t_max) {
                 __stcs(tb, black_moves ? own : opp);
                 __stcs(tw, black_moves ? opp : own);
                 tb += stride; tw += stride;
             }
-            own_r = obf::rev64(own); opp_r = obf::rev64(opp);
-            legal = obf::legal_moves(own, opp, own_r, opp_r);
-            if (legal == 0 && obf::legal_moves(opp, own, opp_r, own_r) == 0) {     // is_game_over (board.py:57-58)
+            legal = obf::legal_moves(own, opp);
+            if (legal == 0 && obf::legal_moves(opp, own) == 0) {     // is_game_over (board.py:57-58)
                 done = true;
                 const u64 fb = black_moves ? own : opp, fw = black_moves ? opp : own;
                 a.nplies[g] = t;
@@ -140,7 +138,8 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                     const unsigned it = ws.item[j];
                     owner = (it >> 8) & 31u; sq = it & 63u;
                     const u64 o = ws.own[owner], p = ws.opp[owner];
-                    const u64 f = obf::flips_for<false, kRowLut>((int)sq, o, p, obf::rev64(o), obf::rev64(p), rays);
+                    
+                    const u64 f = obf::flips_lut((int)sq, o, p, rays, obf::kOpaqueOne);
                     kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, (it & 0x8000u) ? w_s + kW : w_s));
                     before = ws.best_key[owner];
                 }
@@ -167,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                 else if (random_now) move = obf::kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
                 else move = __ffsll((long long)legal) - 1;
                 x = 1ull << move;
-                f = obf::flips_for<false, kRowLut>(move, own, opp, own_r, opp_r, rays);
+                f = obf::flips_lut(move, own, opp, rays, obf::kOpaqueOne);
             }
             if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
             const u64 moved = own | f | x;                    // put_s (board.py:203-208)

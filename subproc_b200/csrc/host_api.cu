@@ -102,7 +102,7 @@ int fail(othello_ctx *c, int rc) { drain(c); return rc; }
 __global__ void __launch_bounds__(32) board_kernel(ob::u64 black, ob::u64 white, int color, int move,
                                                    othello_position_info *out)
 {
-    __shared__ ob::u64 ray_s[obf::kRayTable64];
+    __shared__ ob::u64 ray_s[obf::kRayBasic64];
     ob::fill_rays(ray_s);
     __syncwarp();
     if (threadIdx.x != 0) return;

@@ -55,7 +55,7 @@ __global__ void init_kernel(Ctl *ctl, u64 *own0, u64 *opp0, u64 own, u64 opp, in
 // one breadth-first level, if one is still wanted: frontier[cur] -> frontier[cur ^ 1]
 __global__ void __launch_bounds__(kThreads) expand_kernel(u64 *buf, int64_t cap, Ctl *ctl, int count_leaves)
 {
-    __shared__ u64 ray_s[obf::kRayTable64];
+    __shared__ u64 ray_s[obf::kRayBasic64];
     __shared__ bool s_last;
     // every thread reads the same control words; they are only written by the last CTA of a step
     const unsigned long long n_in = ctl->n;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void dfs_all(const u64 *own, const u64 *opp, unsigned
 __global__ void __launch_bounds__(kThreads) dfs_kernel(const u64 *buf, int64_t cap, Ctl *ctl, unsigned part, unsigned nparts,
                                                        unsigned long long *result)
 {
-    __shared__ u64 ray_s[obf::kRayTable64];
+    __shared__ u64 ray_s[obf::kRayBasic64];
     __shared__ bool s_last;
     fill_rays(ray_s);
     __syncthreads();

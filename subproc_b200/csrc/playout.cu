@@ -20,9 +20,8 @@ using namespace obp;
 namespace {
 
 // Table look-ups on the idle LSU pipe instead of ALU-pipe instructions (A/B on B200, profiles/playout_variants_r02.txt):
-// the two horizontal rays of a flip from the rank tables (+3.8 %), the last three rounds of the k-th-set-bit search
-// from the byte table (+2.3 %)
-constexpr bool kRowLut = true;
+// put() as four line look-ups (obf::flips_lut, +15 % over eight carry-chain rays), the last three rounds of the
+// k-th-set-bit search from the byte table (+2.3 %)
 constexpr bool kKthLut = true;
 
 // the random engine (uniform over puttables()); the greedy engine lives in greedy.cu
@@ -49,12 +48,11 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         __stcs(traj_black + g.off, bm ? g.own : g.opp);
         __stcs(traj_white + g.off, bm ? g.opp : g.own);
     }
-    const u64 own_r = obf::rev64(g.own), opp_r = obf::rev64(g.opp);
-    const u64 legal = obf::legal_moves(g.own, g.opp, own_r, opp_r);
+    const u64 legal = obf::legal_moves(g.own, g.opp);
     int move = OTHELLO_PASS;
     u64 f = 0, x = 0;
     if (legal == 0) {
-        if (obf::legal_moves(g.opp, g.own, opp_r, own_r) == 0) return false;   // is_game_over (board.py:57-58)
+        if (obf::legal_moves(g.opp, g.own) == 0) return false;   // is_game_over (board.py:57-58)
     } else {
         const int n = __popcll(legal);
         const u32 r1 = rng_draw_fma(key, (u32)g.t, 1u, obf::kOpaqueOne);
@@ -63,7 +61,7 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
         // budgets n_rand_* do not change any game played by this kernel.
         move = obf::kth_set_bit<kKthLut>(legal, (int)rng_below(r1, (u32)n), rays);
         x = rays(obf::kRayDirs, move);
-        f = obf::flips_for<true, kRowLut>(move, g.own, g.opp, own_r, opp_r, rays);
+        f = obf::flips_lut(move, g.own, g.opp, rays, obf::kOpaqueOne);
     }
     if (TRAJ == 2 || (TRAJ == 1 && g.t < t_max)) __stcs(traj_move + g.off, (uint8_t)move);
     if (TRAJ) g.off += (unsigned)stride;
@@ -81,7 +79,7 @@ template <int TRAJ, bool UNIFORM>
 __global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
 {
     __shared__ u64 ray_s[obf::kRayTable64];
-    fill_rays(ray_s);
+    fill_rays<obf::kRayTable64>(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
     const int64_t gi = (int64_t)blockIdx.x * kThreads + threadIdx.x;

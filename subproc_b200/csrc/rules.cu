@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kThreads) flips_kernel(const u64 *__restrict__
                                                          const uint8_t *__restrict__ square, u64 *__restrict__ flips,
                                                          int64_t n)
 {
-    __shared__ u64 ray_s[obf::kRayTable64];
+    __shared__ u64 ray_s[obf::kRayBasic64];
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(u64 *__restrict__ black,
                                                         int32_t *__restrict__ ret, uint8_t *__restrict__ flags,
                                                         int64_t n)
 {
-    __shared__ u64 ray_s[obf::kRayTable64];
+    __shared__ u64 ray_s[obf::kRayBasic64];
     fill_rays(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
