@@ -12,10 +12,12 @@ step).  Games are independent, so N GPUs run N shards with no data-path collecti
     e2e     = the same through the host-buffer C ABI (othello_playout_host): start positions come
               from pinned host memory, per-game results (plies, final position) go back to host
               memory, trajectories stay in HBM -- copies inside the timed region
-    roofline= integer roofline of the playout kernel: 512 INT32 lane-ops per position-step
-               against the integer peak measured live by csrc/peak.cu (ALU + FMA pipes
-              co-issuing LOP3 + IMAD; the ALU-pipe-only peak is reported next to it), plus the HBM
-              write-out rate (17 B per position) against MEASURED_PEAKS.json
+    roofline= integer roofline of the playout kernel: frac = executed thread instructions per second
+              (positions/s x the ncu-measured instructions per position, profiles/playout_kernel_costs.json)
+              over the integer issue peak measured live by csrc/peak.cu (ALU + FMA pipes co-issuing
+              LOP3 + IMAD); the canonical 512 INT32 lane-ops per position-step of SURVEY.md 8d are
+              reported next to it as `algorithmic_*` (the kernel executes fewer), plus the HBM write-out
+              rate (17 B per position) against MEASURED_PEAKS.json
     cpu_baseline = the reference's own board.py (oracle/_ref, py3 transcription) playing the same
               kind of games on all host cores for a bounded time (N=1, rank 0 only)
 
@@ -643,6 +645,20 @@ def run_b200_arm(args):
                 "alu_pipe_frac_at_this_runs_rate": kc["alu_pipe_pct"] / 100.0 * scale,
                 "note": "utilisation of the binding pipe (integer ALU) = the ncu figure scaled by this run's "
                         "positions/s over the profiled launch's (the instructions per position are a constant of the kernel)"}
+        # roofline.frac: a utilisation.  The kernel is bound by instruction issue (one warp instruction per clock per
+        # SM sub-partition, which is also what LOP3 + IMAD co-issue reaches: the measured peak) with the ALU pipe as the
+        # busiest pipe behind it.  achieved = executed thread instructions per second = positions/s x the kernel's
+        # executed thread instructions per position (ncu, a constant of the kernel).
+        if executed is not None:
+            roof_achieved = value / n_gpus * executed["thread_inst_per_position"]
+            roof_unit = "Tthread-inst/s"
+            roof_def = ("utilisation of the instruction issue rate: positions/s x executed thread instructions per position "
+                        "(ncu smsp__inst_executed x active lanes / positions of one launch, profiles/playout_kernel_costs.json) "
+                        "over the measured peak of 32-bit integer instruction issue (LOP3 + IMAD co-issued, csrc/peak.cu, "
+                        "measured in this run; 148 SMs x 128 lanes x clock in theory); per GPU")
+        else:
+            roof_achieved, roof_unit = achieved_ops, "Tlane-op/s"
+            roof_def = "algorithm-normalised (profiles/playout_kernel_costs.json missing): see algorithmic_definition"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -654,16 +670,18 @@ def run_b200_arm(args):
                        "l2": "kernel reads no input from HBM; ~%.2f GB written per step exceeds the 126 MB L2"
                              % (pos_per_launch * BYTES_PER_POSITION / 1e9),
                        "parallelism": "games sharded over %d GPU(s), no data-path collective" % n_gpus},
-            "roofline": {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": int_peak / 1e12,
-                         "unit": "Tlane-op/s", "frac": achieved_ops / int_peak, "traffic": traffic,
-                         "frac_definition": "ALGORITHM-normalised throughput, not a utilisation: positions/s x the canonical "
-                                            "512 lane-ops of 8-direction Kogge-Stone (SURVEY.md 8d) over the measured "
-                                            "LOP3+IMAD dual-issue peak; the kernel executes fewer instructions than the "
-                                            "canonical count, so the hardware truth is `executed` (ncu pipe utilisation)",
+            "roofline": {"bound": "int32", "achieved": roof_achieved / 1e12, "peak": int_peak / 1e12,
+                         "unit": roof_unit, "frac": roof_achieved / int_peak, "traffic": traffic,
+                         "frac_definition": roof_def,
+                         "algorithmic_achieved": achieved_ops / 1e12, "algorithmic_frac": achieved_ops / int_peak,
+                         "algorithmic_definition": "positions/s x the canonical 512 lane-ops of 8-direction Kogge-Stone "
+                                                   "(SURVEY.md 8d) over the same peak: ALGORITHM-normalised throughput, not "
+                                                   "a utilisation (above 1 since put() became four table look-ups: the "
+                                                   "kernel executes ~330 instructions per position, 152 of them on the ALU pipe)",
                          "executed": executed,
                          "peak_source": "csrc/peak.cu, measured in this run: LOP3 + IMAD co-issued on the ALU and FMA "
                                         "pipes (the two pipes that execute 32-bit integer lane-ops)",
-                         "peak_alu_pipe_only": int_peak_alu / 1e12, "frac_alu_pipe_only": achieved_ops / int_peak_alu,
+                         "peak_alu_pipe_only": int_peak_alu / 1e12,
                          "algorithmic": "%d INT32 lane-ops per position-step (SURVEY.md 8d)" % LANE_OPS_PER_POSITION,
                          "kernel": "playout_kernel<random,traj>", "kernel_ms": kern_ms,
                          "kernel_ms_definition": "timed region / launches (consecutive launches alternate over two "

@@ -398,6 +398,28 @@ OBF_HD u32 umulhi32(u32 a, u32 b)
     return (u32)(((u64)a * b) >> 32);
 #endif
 }
+// umulhi32(a, b) + c in one IMAD.HI
+OBF_HD u32 madhi32(u32 a, u32 b, u32 c)
+{
+#if defined(__CUDA_ARCH__)
+    u32 d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return umulhi32(a, b) + c;
+#endif
+}
+// byte y (0..7) of the pair (lo, hi) in byte 0 of the result; bytes 1..3 are junk (byte 0 of lo)
+OBF_HD u32 byte_of(u32 lo, u32 hi, u32 y)
+{
+#if defined(__CUDA_ARCH__)
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(y));     // (no masking of the selector: y < 8)
+    return d;
+#else
+    return byte_perm(lo, hi, y);
+#endif
+}
 
 // put() entirely by table look-up: the FOUR lines through the move (rank, file, two diagonals) instead of eight rays.
 // Each line is gathered into a byte per colour, [position][opponent byte] gives the squares where an own disc would
@@ -422,8 +444,8 @@ OBF_HD u64 flips_lut(int s, u64 own, u64 opp, const RayTable &T, u32 one)
     const u32 shr24 = one << 8;                                  // v >> 24 == umulhi(v, 1 << 8)
     u32 f_lo, f_hi;
     {   // the rank
-        const u32 ob = byte_perm(olo, ohi, y);                   // byte 0 = the rank (bytes 1..3: junk)
-        const u32 pb = byte_perm(plo, phi, y) & 0xffu;
+        const u32 ob = byte_of(olo, ohi, y);                     // byte 0 = the rank (bytes 1..3: junk)
+        const u32 pb = byte_of(plo, phi, y) & 0xffu;
         const u32 flip = T.byte((T.byte(pb * one + t1x) & ob) * one + t2x);
         const u64 mul = T.word(kRankMul64 + y);
         f_lo = flip * lo32(mul);
@@ -433,8 +455,8 @@ OBF_HD u64 flips_lut(int s, u64 own, u64 opp, const RayTable &T, u32 one)
         const u64 fm = T.word(kFileMul64 + x);
         const u32 up = lo32(fm);
         const u32 kLo = 0x02040810u, kHi = 0x20408100u;          // bits 8k+7 -> bit k / bit 4+k of the high half
-        const u32 pb = (umulhi32((plo * up) & 0x80808080u, kLo) + umulhi32((phi * up) & 0x80808080u, kHi)) & 0xffu;
-        const u32 ob = umulhi32((olo * up) & 0x80808080u, kLo) + umulhi32((ohi * up) & 0x80808080u, kHi);   // (junk above bit 7)
+        const u32 pb = madhi32((plo * up) & 0x80808080u, kLo, umulhi32((phi * up) & 0x80808080u, kHi)) & 0xffu;
+        const u32 ob = madhi32((olo * up) & 0x80808080u, kLo, umulhi32((ohi * up) & 0x80808080u, kHi));   // (junk above bit 7)
         const u32 flip = T.byte((T.byte(pb * one + t1y) & ob) * one + t2y);
         const u64 col = T.word(kSpread64 + flip);
         f_lo += lo32(col) * hi32(fm);

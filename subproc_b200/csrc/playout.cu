@@ -76,7 +76,10 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
 // UNIFORM: no per-game turn0 -- every game starts with Black, so the loop is unrolled over the two colours
 template <int TRAJ, bool UNIFORM>
 // (128 threads x >= 10 CTAs per SM measured best on B200: 64/128/256 threads and 9..12 CTAs are within 2 %)
-__global__ void __launch_bounds__(kThreads, 10) playout_kernel(const othello_playout_args a)
+#if !defined(OB_PLAYOUT_CTAS)
+#define OB_PLAYOUT_CTAS 10
+#endif
+__global__ void __launch_bounds__(kThreads, OB_PLAYOUT_CTAS) playout_kernel(const othello_playout_args a)
 {
     __shared__ u64 ray_s[obf::kRayTable64];
     fill_rays<obf::kRayTable64>(ray_s);
