@@ -29,6 +29,7 @@ struct WarpScratch {
     u64 own[32], opp[32];                     // positions of the 32 games (mover-relative)
     unsigned best_key[32];                    // arg-max state per game
     unsigned best_sq[32];
+    unsigned row[32];                         // float offset of the children's weight row: colour table + 10 * phase
     unsigned short item[kMaxItems];           // (White to move << 15) | (game lane << 8) | square
 };
 
@@ -40,7 +41,10 @@ __device__ __forceinline__ unsigned ordered_bits(float v)
 }
 
 template <bool SUBST, bool TRAJ>
-__global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playout_args a)
+#if !defined(OB_GREEDY_CTAS)
+#define OB_GREEDY_CTAS 7
+#endif
+__global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const othello_playout_args a)
 {
     constexpr int kW = OTHELLO_PHASES * OTHELLO_WEIGHTS;
     __shared__ float w_s[2 * kW];                             // Black's table, then White's
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
         if (total > 0) {
             ws.own[lane] = own; ws.opp[lane] = opp;
             ws.best_key[lane] = 0u; ws.best_sq[lane] = 64u;
+            ws.row[lane] = (black_moves ? 0 : kW) + 10 * phase_row(__popcll(own | opp) + 1);
             if (evaluate) {
                 int idx = incl - cnt;
                 for (u64 rem = legal; rem; rem &= rem - 1)
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 6) greedy_kernel(const othello_playo
                     const u64 o = ws.own[owner], p = ws.opp[owner];
                     
                     const u64 f = obf::flips_lut((int)sq, o, p, rays, obf::kOpaqueOne);
-                    kbits = ordered_bits(eval_fast(o | f | (1ull << sq), p & ~f, (it & 0x8000u) ? w_s + kW : w_s));
+                    kbits = ordered_bits(eval_row(o | f | (1ull << sq), p & ~f, w_s + ws.row[owner]));
                     before = ws.best_key[owner];
                 }
                 __syncwarp();
