@@ -155,3 +155,38 @@ def test_kth_set_bit_table(fb):
         bits = [i for i in range(8) if (v >> i) & 1]
         for k, want in enumerate(bits):
             assert fb.fb_kth_table(v, k) == want
+
+
+def test_line_tables_every_square_line_and_pattern(fb, oracle):
+    """put() by line look-ups (obf::flips_lut, what the game kernels run): for every square and each of the four
+    lines through it (rank, file, both diagonals) all 3^(L-1) fillings of the other squares of the line, the rest of
+    the board filled at random -- the gathers (PRMT / multiplies), both tables and the scatters against the oracle"""
+    rng = np.random.RandomState(11)
+    own_l, opp_l, sq_l = [], [], []
+    for s in range(64):
+        x, y = s & 7, s >> 3
+        for dx, dy in ((1, 0), (0, 1), (1, 1), (1, -1)):
+            line = [(x + k * dx) + 8 * (y + k * dy) for k in range(-7, 8)
+                    if k != 0 and 0 <= x + k * dx < 8 and 0 <= y + k * dy < 8]
+            if not line:                                       # the one-square diagonal of a corner
+                continue
+            pats = np.array(np.meshgrid(*[[0, 1, 2]] * len(line), indexing='ij')).reshape(len(line), -1).T
+            o = np.zeros(len(pats), dtype=np.uint64)
+            p = np.zeros(len(pats), dtype=np.uint64)
+            keep = ~np.uint64(1 << s)
+            for j, c in enumerate(line):
+                o |= (pats[:, j] == 1).astype(np.uint64) << np.uint64(c)
+                p |= (pats[:, j] == 2).astype(np.uint64) << np.uint64(c)
+                keep &= ~np.uint64(1 << c)
+            occ = rng.randint(0, 2 ** 62, size=len(pats)).astype(np.uint64) << np.uint64(2) | rng.randint(0, 4, size=len(pats)).astype(np.uint64)
+            col = rng.randint(0, 2 ** 62, size=len(pats)).astype(np.uint64) << np.uint64(2) | rng.randint(0, 4, size=len(pats)).astype(np.uint64)
+            own_l.append(o | (occ & col & keep))
+            opp_l.append(p | (occ & ~col & keep))
+            sq_l.append(np.full(len(pats), s, dtype=np.uint8))
+    own = np.ascontiguousarray(np.concatenate(own_l)); opp = np.ascontiguousarray(np.concatenate(opp_l))
+    sq = np.ascontiguousarray(np.concatenate(sq_l))
+    assert own.size > 300000 and not np.any(own & opp)
+    out = np.zeros(own.size, dtype=np.uint64)
+    fb.fb_flips_lut(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))
+    _, _, want, _ = oracle.put(own, opp, 1, sq)
+    assert np.array_equal(out, want)
