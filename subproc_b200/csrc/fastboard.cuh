@@ -101,18 +101,9 @@ OBF_HD Inter ior(Inter x, Inter y) { return Inter{x.a | y.a, x.b | y.b}; }
 static __device__ __constant__ u32 kOpaqueOne = 1u;
 #endif
 
-// v >> 1; on the device optionally as the high half of a multiply by an opaque 1 << 31 (IMAD.HI, FMA pipe)
-OBF_HD u32 shr1(u32 v)
-{
-#if defined(__CUDA_ARCH__) && defined(OBF_SHR_FMA)
-    return __umulhi(v, kOpaqueOne << 31);
-#else
-    return v >> 1;
-#endif
-}
 template <int D> OBF_HD Inter ishift(Inter v)        // D squares up (towards higher squares), D in {7, 8, 9}
 {
-    return D == 8 ? Inter{v.b << 8, v.a} : D == 9 ? Inter{v.b << 9, v.a << 1} : Inter{v.b << 7, shr1(v.a)};
+    return D == 8 ? Inter{v.b << 8, v.a} : D == 9 ? Inter{v.b << 9, v.a << 1} : Inter{v.b << 7, v.a >> 1};
 }
 template <int D> OBF_HD Inter ishift2(Inter v)       // 2 * D squares up
 {
