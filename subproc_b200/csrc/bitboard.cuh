@@ -105,7 +105,7 @@ struct Rays {
 
 // the table is built at compile time and lives in global memory (L2-resident); a CTA copies its 2 KB
 // into shared memory with two loads per thread instead of walking 256 rays
-struct RayTableInit {
+struct alignas(16) RayTableInit {
     u64 v[obf::kRayTable64];
     constexpr RayTableInit() : v()
     {
@@ -120,6 +120,29 @@ template <int N = obf::kRayBasic64>
 __device__ __forceinline__ void fill_rays(u64 *t)
 {
     for (int i = threadIdx.x; i < N; i += blockDim.x) t[i] = kRayTable.v[i];
+}
+
+// The whole table for a game kernel, t 16-byte aligned, CTAs of at least MIN_THREADS threads: 16-byte loads, ALL of
+// them issued before the first store.  A plain copy loop is one L2 round trip per 8 bytes and thread, twelve in a row
+// for 11.9 KB and 128 threads: ncu's samples had the warps of the playout kernel spend 13 % of their life there.
+template <int MIN_THREADS>
+__device__ __forceinline__ void fill_tables(u64 *t)
+{
+    constexpr int kVec = obf::kRayTable64 / 2, kPer = (kVec + MIN_THREADS - 1) / MIN_THREADS;
+    static_assert(obf::kRayTable64 % 2 == 0, "table size");
+    const uint4 *src = reinterpret_cast<const uint4 *>(kRayTable.v);
+    uint4 *dst = reinterpret_cast<uint4 *>(t);
+    uint4 r[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const int i = threadIdx.x + j * blockDim.x;
+        if (i < kVec) r[j] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const int i = threadIdx.x + j * blockDim.x;
+        if (i < kVec) dst[i] = r[j];
+    }
 }
 
 // Board.put(piece, x, y) (board.py:161-174): flips of an own disc on EMPTY square s

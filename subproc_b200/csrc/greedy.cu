@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
 {
     constexpr int kW = OTHELLO_PHASES * OTHELLO_WEIGHTS;
     __shared__ float w_s[2 * kW];                             // Black's table, then White's
-    __shared__ u64 ray_s[obf::kRayTable64];
+    __shared__ __align__(16) u64 ray_s[obf::kRayTable64];
     __shared__ WarpScratch scratch[kWarps];
     for (int i = threadIdx.x; i < 2 * kW; i += blockDim.x) {    // (a CTA is 2 or 4 warps, see ob_launch_greedy)
         const float *src = i < kW ? (a.weights ? a.weights : a.weights_white)
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
     // which colours are served by the greedy engine (the other answers uniformly at random)
     const bool greedy_b = a.policy == OTHELLO_POLICY_GREEDY;
     const bool greedy_w = (a.policy_white == -1 ? a.policy : a.policy_white) == OTHELLO_POLICY_GREEDY;
-    fill_rays<obf::kRayTable64>(ray_s);
+    ob::fill_tables<kThreads / 2>(ray_s);                     // (a CTA is 2 or 4 warps)
     __syncthreads();
     const Rays rays = {ray_s};
     WarpScratch &ws = scratch[threadIdx.x >> 5];
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
                 tb += stride; tw += stride;
             }
             legal = obf::legal_moves(own, opp);
-            if (legal == 0 && obf::legal_moves(opp, own) == 0) {     // is_game_over (board.py:57-58)
+            // is_game_over (board.py:57-58); a full board needs no second move generation
+            if (legal == 0 && (~(own | opp) == 0 || obf::legal_moves(opp, own) == 0)) {
                 done = true;
                 const u64 fb = black_moves ? own : opp, fw = black_moves ? opp : own;
                 a.nplies[g] = t;

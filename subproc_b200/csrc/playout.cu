@@ -29,13 +29,16 @@ struct Game {
     u64 own, opp;
     unsigned off;               // element index t * stride + game into the three trajectory arrays
     int t;
+    bool passed;                // the previous ply was a pass
 };
 
 // One ply.  BLACK: 1 = Black moves, 0 = White moves (known at compile time when every game of the
 // launch starts with the same colour: Black and White then alternate strictly, passes included),
 // -1 = read `black_moves`.  Returns false when the game is over.
-// TRAJ: 0 = no trajectory; 1 = trajectory with capacity checks; 2 = a trajectory that is known to fit (standard
-// opening and t_max >= 120: 60 moves + at most 60 interleaved passes), so the two checks per ply fall away.
+// TRAJ: 0 = no trajectory; 1 = trajectory with capacity checks; 2 = a trajectory that is known to fit, so the two
+// checks per ply fall away: from the standard opening the first two plies are moves and a pass can only follow a move,
+// so a game has at most 60 moves + 59 passes = 119 plies; with the pass that is taken back at the end of a game (below)
+// the kernel writes position rows 0 .. plies + 1 <= 120 and move rows 0 .. plies <= 119, i.e. t_max >= 120 holds them.
 // The three trajectory arrays are addressed with ONE 32-bit element index t * stride + game (a 32-bit add per
 // ply instead of three 64-bit pointer increments), hence (t_max + 2) * stride < 2^32 (othello_playout checks).
 template <int TRAJ, int BLACK>
@@ -52,8 +55,15 @@ __device__ __forceinline__ bool play_ply(Game &g, bool black_moves, u32 key, int
     int move = OTHELLO_PASS;
     u64 f = 0, x = 0;
     if (legal == 0) {
-        if (obf::legal_moves(g.opp, g.own) == 0) return false;   // is_game_over (board.py:57-58)
+        // is_game_over (board.py:57-58) needs the other colour's moves -- which the NEXT ply computes anyway, with the
+        // whole warp instead of the few lanes that are here (that second move generation ran 6 % of the kernel's warp
+        // instructions at 7 active lanes, profiles/playout_segments_r02.txt).  So the ply is played as a pass; if the
+        // next one finds no move either, the game was over before the pass: it is taken back (rows past a game's
+        // end are unspecified, and the rows up to it are what they would have been).
+        if (g.passed) { g.t--; return false; }
+        g.passed = true;
     } else {
+        g.passed = false;
         const int n = __popcll(legal);
         const u32 r1 = rng_draw_fma(key, (u32)g.t, 1u, obf::kOpaqueOne);
         // go_for's substitution (game_runner.py:134-150) replaces the engine's move by a uniformly
@@ -81,8 +91,8 @@ template <int TRAJ, bool UNIFORM>
 #endif
 __global__ void __launch_bounds__(kThreads, OB_PLAYOUT_CTAS) playout_kernel(const othello_playout_args a)
 {
-    __shared__ u64 ray_s[obf::kRayTable64];
-    fill_rays<obf::kRayTable64>(ray_s);
+    __shared__ __align__(16) u64 ray_s[obf::kRayTable64];
+    ob::fill_tables<kThreads>(ray_s);
     __syncthreads();
     const Rays rays = {ray_s};
     const int64_t gi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -95,6 +105,7 @@ __global__ void __launch_bounds__(kThreads, OB_PLAYOUT_CTAS) playout_kernel(cons
         Game g;
         g.own = black_moves ? b0 : w0; g.opp = black_moves ? w0 : b0;
         g.t = 0;
+        g.passed = false;
         g.off = (unsigned)gi;
         const u32 key = rng_key(a.seed, a.gid0 + (u64)gi);
         const int t_max = a.t_max;
