@@ -131,9 +131,19 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
             ws.best_key[lane] = 0u; ws.best_sq[lane] = 64u;
             ws.row[lane] = (black_moves ? 0 : kW) + 10 * phase_row(__popcll(own | opp) + 1);
             if (evaluate) {
-                int idx = incl - cnt;
-                for (u64 rem = legal; rem; rem &= rem - 1)
-                    ws.item[idx++] = (unsigned short)((black_moves ? 0 : 0x8000) | (lane << 8) | (__ffsll((long long)rem) - 1));
+                // one 32-bit half after the other: 9 instructions per square (lowest bit through POPC of the bits
+                // below it) instead of the 21 of a 64-bit find-first-set + clear
+                unsigned short *dst = ws.item + (incl - cnt);
+                unsigned tag = (black_moves ? 0u : 0x8000u) | ((unsigned)lane << 8);
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    for (u32 w = half ? obf::hi32(legal) : obf::lo32(legal); w;) {
+                        const u32 below = w - 1u;
+                        *dst++ = (unsigned short)(tag + (unsigned)__popc(~w & below));
+                        w &= below;
+                    }
+                    tag += 32u;
+                }
             }
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
