@@ -553,7 +553,7 @@ def run_b200_arm(args):
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     e2e_gid = [gid_base + (W + K + 3) * G]
 
-    def e2e_run(steps, full=False):
+    def e2e_run(steps, full=False, upload=True):
         """issue step i+1, then collect step i; returns the positions played (from the batch totals)"""
         tickets = [0, 0]
         played = 0
@@ -562,7 +562,8 @@ def run_b200_arm(args):
                 o = h_out[i % 2]
                 tk = ctypes.c_int64()
                 _lib.check(L.othello_playout_host_async(
-                    ctx, 1, e2e_gid[0], G, P(h_b0), P(h_w0), None, ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX,
+                    ctx, 1, e2e_gid[0], G, P(h_b0) if upload else None, P(h_w0) if upload else None, None,
+                    ops.POLICY_RANDOM, 0, 0, 0, None, -1, None, T_MAX,
                     None, None, None, P(o[2]) if full else None, P(o[3]) if full else None, P(o[4]) if full else None,
                     None if full else P(o[0]), P(o[1]), ctypes.byref(tk)), "othello_playout_host_async")
                 e2e_gid[0] += G
@@ -572,11 +573,11 @@ def run_b200_arm(args):
                 played += int(h_out[(i - 1) % 2][1][0])                  # the step's result, read on the host
         return played
 
-    def e2e_timed(full):
-        e2e_run(max(3, min(W, 5)), full)
+    def e2e_timed(full, upload=True):
+        e2e_run(max(3, min(W, 5)), full, upload)
         barrier()
         t0 = time.perf_counter()
-        played = e2e_run(K, full)
+        played = e2e_run(K, full, upload)
         torch.cuda.synchronize()
         return played, time.perf_counter() - t0
 
@@ -588,6 +589,9 @@ def run_b200_arm(args):
               int((sm >> 8).astype("uint8").view("int8").sum()) == int(last[1][1]) and int((sm & 0xff).min()) > 0)
     full_positions, full_s = e2e_timed(True)                             # 20 B per game back instead of 2
     e2e_ok = e2e_ok and int(last[2].sum(dtype=torch.int64)) == int(last[1][0])
+    # what GameRunner.play_a_game itself does (game_runner.py:165-170: every game starts from a fresh Board()): no start
+    # positions to upload (NULL = the standard opening), two-byte summaries + totals back
+    std_positions, std_s = e2e_timed(False, upload=False)
     # a single synchronous call (copy-in, kernels, copy-out, wait): the latency of one batch
     sync_ms = []
     for i in range(5):
@@ -609,14 +613,14 @@ def run_b200_arm(args):
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s * 1e3, full_s * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s * 1e3, full_s * 1e3, std_s * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([positions, games, e2e_positions, full_positions], dtype=torch.float64, device=dev)
+        c = torch.tensor([positions, games, e2e_positions, full_positions, std_positions], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms, full_ms = float(t[0]), float(t[1]), float(t[2])
-        positions, games, e2e_positions, full_positions = float(c[0]), float(c[1]), float(c[2]), float(c[3])
+        total_ms, e2e_ms, full_ms, std_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        positions, games, e2e_positions, full_positions, std_positions = (float(c[i]) for i in range(5))
     else:
-        e2e_ms, full_ms = e2e_s * 1e3, full_s * 1e3
+        e2e_ms, full_ms, std_ms = e2e_s * 1e3, full_s * 1e3, std_s * 1e3
 
     if rank == 0:
         value = positions / (total_ms * 1e-3)
@@ -699,6 +703,13 @@ def run_b200_arm(args):
                                      "d2h_bytes_per_step": G * 20 + 32,
                                      "what": "the same with plies (int32) + final position (2 x u64) per game instead "
                                              "of the two-byte summary"},
+                    "standard_opening": {"value": std_positions / (std_ms * 1e-3), "unit": UNIT,
+                                         "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
+                                         "what": "the same without the upload: start positions NULL = every game from "
+                                                 "the standard opening, as GameRunner.play_a_game does "
+                                                 "(game_runner.py:165-170); on an 8-GPU host whose PCIe fabric gives "
+                                                 "each GPU ~24 GB/s the 16 B per game of the headline cost ~0.7 ms per "
+                                                 "step next to a ~0.73 ms kernel"},
                     "api": "othello_playout_host_async + othello_ctx_wait (C ABI, pinned host buffers, two batches "
                            "in flight; start positions uploaded (16 B per game), two-byte per-game summaries + batch "
                            "totals downloaded every step; trajectories stay in HBM); sync_call_ms = one synchronous "
