@@ -77,7 +77,7 @@ __device__ __forceinline__ int phase_row(int discs)
 __device__ __forceinline__ void features10(u64 own, u64 opp, int f[10])
 {
     f[0] = __popcll(own | opp);
-    f[1] = __popcll(obf::legal_moves(own, opp));
+    f[1] = obf::mobility(own, opp);
 #pragma unroll
     for (int k = 0; k < 8; k++) f[2 + k] = class_count(own, k);
 }
@@ -88,7 +88,7 @@ __device__ __forceinline__ float eval_linear(u64 own, u64 opp, const float *__re
     const int discs = __popcll(own | opp);
     const float *row = w + 10 * phase_row(discs);
     float acc = row[9];
-    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
+    acc = fmaf(row[0], (float)obf::mobility(own, opp), acc);
 #pragma unroll
     for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)class_count(own, k), acc);
     return acc;

@@ -188,6 +188,9 @@ OBF_HD int popc_inter(Inter v)
 
 // Board.puttables(piece) as a mask (board.py:46-52).
 OBF_HD u64 legal_moves(u64 own, u64 opp) { return from_inter(legal_inter(make_pos4(own, opp))); }
+// n_puttable_for(piece) (board.py:54-55): a popcount does not care about the layout, so the mask is not converted back
+// (two PRMT on the ALU pipe fewer than __popcll(legal_moves()))
+OBF_HD int mobility(u64 own, u64 opp) { return popc_inter(legal_inter(make_pos4(own, opp))); }
 
 // n_puttable_for(mover) AFTER the mover has played: `placed` = the new disc + the discs it flipped.  The
 // successor is built from the prepared parent (own' = own | placed, opp' = opp & ~placed), so a child costs one

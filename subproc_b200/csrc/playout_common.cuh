@@ -19,7 +19,7 @@ __device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__rest
     const int discs = __popcll(own | opp);
     const float *row = w + 10 * ob::phase_row(discs);
     float acc = row[9];
-    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
+    acc = fmaf(row[0], (float)obf::mobility(own, opp), acc);
 #pragma unroll
     for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)ob::class_count(own, k), acc);
     return acc;
@@ -30,7 +30,7 @@ __device__ __forceinline__ float eval_fast(u64 own, u64 opp, const float *__rest
 __device__ __forceinline__ float eval_row(u64 own, u64 opp, const float *__restrict__ row)
 {
     float acc = row[9];
-    acc = fmaf(row[0], (float)__popcll(obf::legal_moves(own, opp)), acc);
+    acc = fmaf(row[0], (float)obf::mobility(own, opp), acc);
 #pragma unroll
     for (int k = 0; k < 8; k++) acc = fmaf(row[1 + k], (float)ob::class_count(own, k), acc);
     return acc;

@@ -27,7 +27,7 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ u64 pack_features(u64 side, u64 other)
 {
     u64 k = (u64)__popcll(side | other);
-    k = (k << 6) | (u64)__popcll(obf::legal_moves(side, other));
+    k = (k << 6) | (u64)obf::mobility(side, other);
     k = (k << 3) | (u64)class_count(side, 0);
     k = (k << 4) | (u64)class_count(side, 1);
     k = (k << 3) | (u64)class_count(side, 2);

@@ -50,6 +50,11 @@ extern "C" void fb_mobility_both(const unsigned long long *black, const unsigned
     for (long i = 0; i < n; i++) obf::mobility_both(black[i], white[i], mb[i], mw[i]);
 }
 
+extern "C" void fb_mobility(const unsigned long long *own, const unsigned long long *opp, int *out, long n)
+{
+    for (long i = 0; i < n; i++) out[i] = obf::mobility(own[i], opp[i]);
+}
+
 extern "C" void fb_child_mobility(const unsigned long long *own, const unsigned long long *opp, const unsigned char *sq,
                                   int *out, long n)
 {

@@ -95,6 +95,11 @@ def test_mobility_of_both_colours_in_one_pass(fb, oracle):
     fb.fb_mobility_both(P(b), P(w), P(mb), P(mw), ctypes.c_long(n))
     pop = lambda a: np.array([bin(int(v)).count("1") for v in a], dtype=np.int32)
     assert np.array_equal(mb, pop(oracle.puttables(b, w, 1))) and np.array_equal(mw, pop(oracle.puttables(b, w, 2)))
+    # obf::mobility (one colour, mask never converted back to the standard layout): what counts() / the evaluation use
+    m1, m2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    fb.fb_mobility(P(b), P(w), P(m1), ctypes.c_long(n))
+    fb.fb_mobility(P(w), P(b), P(m2), ctypes.c_long(n))
+    assert np.array_equal(m1, mb) and np.array_equal(m2, mw)
 
 
 def test_child_mobility_from_the_prepared_parent(fb, oracle):
