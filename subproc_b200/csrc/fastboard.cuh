@@ -225,10 +225,20 @@ constexpr int kFileMul64 = kRankMul64 + 8;             // [8]: low word 1 << (7 
 constexpr int kDiag9_64 = kFileMul64 + 8;              // [64]: the whole +9 / -9 diagonal through a square
 constexpr int kDiag7_64 = kDiag9_64 + 64;              // [64]: the whole +7 / -7 diagonal
 constexpr int kRowOutflank64 = kDiag7_64 + 64;         // bytes [position on the line][opponent discs of the line]
-constexpr int kRowFlip64 = kRowOutflank64 + 8 * 256 / 8;   // bytes [position on the line][outflanking own discs]
-constexpr int kKthBit64 = kRowFlip64 + 8 * 256 / 8;    // bytes [byte value][k]: position of the k-th set bit of a byte
+// The two line tables are rows of 256 bytes, one per position on the line, kLineStride bytes apart.  With rows 256 bytes
+// apart the shared-memory bank of an entry would depend on the pattern alone, and the patterns are anything but uniform
+// (the second look-up is indexed by at most two closing discs: 0, 1, 2, 4 ...): lanes with different positions and the
+// same pattern -- different addresses in ONE bank -- made these byte loads 6 to 7.6 wavefronts each, and the greedy kernel,
+// which does eight of them per successor, ran at 87 % of the shared-memory pipe (profiles/greedy_r02_ncu_summary.txt).
+// 276 = 256 + 20 moves every row on by five banks.
+constexpr int kLineStride = 276;
+constexpr int kLineTable64 = (8 * kLineStride + 7) / 8;
+constexpr int kRowFlip64 = kRowOutflank64 + kLineTable64;  // bytes [position on the line][outflanking own discs]
+constexpr int kKthBit64 = kRowFlip64 + kLineTable64;   // bytes [byte value][k]: position of the k-th set bit of a byte
 constexpr int kSpread64 = kKthBit64 + 256 * 8 / 8;     // [256]: bit k of the index on bit 8 * k (a file-a column)
-constexpr int kRayTable64 = kSpread64 + 256;           // table entries (u64): 11.9 KB
+constexpr int kLine9_64 = kSpread64 + 256;             // [15]: the +9 / -9 diagonal number x - y + 7
+constexpr int kLine7_64 = kLine9_64 + 15;              // [15]: the +7 / -7 diagonal number x + y
+constexpr int kRayTable64 = kLine7_64 + 15;            // table entries (u64): 12.2 KB
 OBF_HD constexpr u64 make_ray(int d, int s)
 {
     if (d == kRayDirs) return 1ull << s;                               // row 4: the square itself (1 << s as a table load)
@@ -289,6 +299,8 @@ OBF_HD constexpr u64 make_table_word(int i)
     if (i < kDiag9_64) return ((1ull << (i - kFileMul64)) << 32) | (1ull << (7 - (i - kFileMul64)));
     if (i < kDiag7_64) return make_diagonal(9, i - kDiag9_64);
     if (i < kRowOutflank64) return make_diagonal(7, i - kDiag7_64);
+    if (i >= kLine7_64) { const int n = i - kLine7_64; return make_diagonal(7, n < 8 ? n : 8 * (n - 7) + 7); }   // a square with x + y = n
+    if (i >= kLine9_64) { const int n = i - kLine9_64; return make_diagonal(9, n < 8 ? 8 * (7 - n) : n - 7); }   // ... x - y + 7 = n
     u64 w = 0;
     for (int j = 0; j < 8; j++) {
         if (i >= kSpread64) {
@@ -296,11 +308,11 @@ OBF_HD constexpr u64 make_table_word(int i)
         } else if (i >= kKthBit64) {
             w |= (u64)kth_bit_of_byte((u32)(i - kKthBit64), j) << (8 * j);
         } else if (i < kRowFlip64) {
-            const int e = (i - kRowOutflank64) * 8 + j;
-            w |= (u64)row_outflank(e >> 8, (u32)(e & 0xff)) << (8 * j);
+            const int e = (i - kRowOutflank64) * 8 + j, x = e / kLineStride, v = e % kLineStride;
+            if (x < 8 && v < 256) w |= (u64)row_outflank(x, (u32)v) << (8 * j);
         } else {
-            const int e = (i - kRowFlip64) * 8 + j;
-            w |= (u64)row_flipped(e >> 8, (u32)(e & 0xff)) << (8 * j);
+            const int e = (i - kRowFlip64) * 8 + j, x = e / kLineStride, v = e % kLineStride;
+            if (x < 8 && v < 256) w |= (u64)row_flipped(x, (u32)v) << (8 * j);
         }
     }
     return w;
@@ -317,8 +329,8 @@ OBF_HD void row_flips(int s, u64 own, u64 opp, const RayTable &rays, u32 &f_lo, 
     const u32 y = (u32)s >> 3, x = (u32)s & 7u;
     const u32 ob = byte_perm(lo32(own), hi32(own), y);       // byte 0 = the rank of the move (bytes 1..3: the first rank)
     const u32 pb = byte_perm(lo32(opp), hi32(opp), y);
-    const u32 cand = rays.byte(kRowOutflank64 * 8 + x * 256 + (pb & 0xffu));
-    const u32 flip = rays.byte(kRowFlip64 * 8 + x * 256 + (cand & ob));
+    const u32 cand = rays.byte(kRowOutflank64 * 8 + x * kLineStride + (pb & 0xffu));
+    const u32 flip = rays.byte(kRowFlip64 * 8 + x * kLineStride + (cand & ob));
     const u64 mul = rays.word(kRankMul64 + y);
     f_lo += flip * lo32(mul);
     f_hi += flip * hi32(mul);
@@ -437,13 +449,16 @@ OBF_HD u32 byte_of(u32 lo, u32 hi, u32 y)
 // and a byte with junk above it needs no cleaning where it is ANDed with a clean table byte.  27 ALU-pipe
 // instructions for a move instead of 52, no rotated board, no POPC.  `one` = kOpaqueOne on the device (keeps the
 // shifts and address additions on the FMA pipe), 1 on the host.
-template <typename RayTable>
+// LINE_DIAG: fetch the diagonal masks by diagonal number (15 entries each: lanes on the same diagonal share a word and
+// the rest fall into different banks) instead of by square (64 entries: 4.8 wavefronts per load in the greedy kernel, which
+// is bound by the shared-memory pipe); costs two IMADs, so the random playout kernel, whose LSU pipe idles, keeps the squares.
+template <bool LINE_DIAG = false, typename RayTable>
 OBF_HD u64 flips_lut(int s, u64 own, u64 opp, const RayTable &T, u32 one)
 {
     const u32 y = (u32)s >> 3, x = (u32)s & 7u;
     const u32 olo = lo32(own), ohi = hi32(own), plo = lo32(opp), phi = hi32(opp);
-    const u32 t1x = kRowOutflank64 * 8 + x * 256, t2x = kRowFlip64 * 8 + x * 256;      // tables of position x
-    const u32 t1y = kRowOutflank64 * 8 + y * 256, t2y = kRowFlip64 * 8 + y * 256;
+    const u32 t1x = kRowOutflank64 * 8 + x * kLineStride, t2x = kRowFlip64 * 8 + x * kLineStride;      // tables of position x
+    const u32 t1y = kRowOutflank64 * 8 + y * kLineStride, t2y = kRowFlip64 * 8 + y * kLineStride;
     const u32 shr24 = one << 8;                                  // v >> 24 == umulhi(v, 1 << 8)
     u32 f_lo, f_hi;
     {   // the rank
@@ -465,17 +480,17 @@ OBF_HD u64 flips_lut(int s, u64 own, u64 opp, const RayTable &T, u32 one)
         f_lo += lo32(col) * hi32(fm);
         f_hi += hi32(col) * hi32(fm);
     }
-#define OBF_DIAGONAL(TABLE)                                                                                        \
+#define OBF_DIAGONAL(INDEX)                                                                                        \
     {                                                                                                              \
-        const u64 d = T.word((TABLE) + (u32)s);                                                                    \
+        const u64 d = T.word(INDEX);                                                                               \
         const u32 pb = umulhi32(((plo & lo32(d)) | (phi & hi32(d))) * 0x01010101u, shr24);                         \
         const u32 ob = umulhi32(((olo & lo32(d)) | (ohi & hi32(d))) * 0x01010101u, shr24);                         \
         const u32 r = T.byte((T.byte(pb * one + t1x) & ob) * one + t2x) * 0x01010101u;                            \
         f_lo |= r & lo32(d);                                                                                       \
         f_hi |= r & hi32(d);                                                                                       \
     }
-    OBF_DIAGONAL(kDiag9_64)
-    OBF_DIAGONAL(kDiag7_64)
+    OBF_DIAGONAL(LINE_DIAG ? (x * one + (kLine9_64 + 7)) - y * one : kDiag9_64 + (u32)s)
+    OBF_DIAGONAL(LINE_DIAG ? x * one + (y * one + kLine7_64) : kDiag7_64 + (u32)s)
 #undef OBF_DIAGONAL
     return pack(f_lo, f_hi);
 }

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
                     owner = (it >> 8) & 31u; sq = it & 63u;
                     const u64 o = ws.own[owner], p = ws.opp[owner];
                     
-                    const u64 f = obf::flips_lut((int)sq, o, p, rays, obf::kOpaqueOne);
+                    const u64 f = obf::flips_lut<true>((int)sq, o, p, rays, obf::kOpaqueOne);
                     kbits = ordered_bits(eval_row(o | f | (1ull << sq), p & ~f, w_s + ws.row[owner]));
                     before = ws.best_key[owner];
                 }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, OB_GREEDY_CTAS) greedy_kernel(const 
                 else if (random_now) move = obf::kth_set_bit(legal, (int)rng_below(rng_draw(key, (u32)t, 1u), (u32)n));
                 else move = __ffsll((long long)legal) - 1;
                 x = 1ull << move;
-                f = obf::flips_lut(move, own, opp, rays, obf::kOpaqueOne);
+                f = obf::flips_lut<true>(move, own, opp, rays, obf::kOpaqueOne);
             }
             if (TRAJ && t < t_max) { __stcs(tm, (uint8_t)move); tm += stride; }
             const u64 moved = own | f | x;                    // put_s (board.py:203-208)

@@ -78,6 +78,17 @@ extern "C" void fb_flips_lut(const unsigned long long *own, const unsigned long 
     }
 }
 
+// ... with the diagonal masks fetched by diagonal number (what the greedy kernel runs)
+extern "C" void fb_flips_lut_line(const unsigned long long *own, const unsigned long long *opp, const unsigned char *sq,
+                             unsigned long long *out, long n)
+{
+    init();
+    for (long i = 0; i < n; i++) {
+        const unsigned long long x = 1ull << sq[i];
+        out[i] = ((own[i] | opp[i]) & x) ? 0ull : obf::flips_lut<true>(sq[i], own[i], opp[i], Rays(), 1u);
+    }
+}
+
 // byte [value][k] of the k-th-set-bit table the playout kernel reads from shared memory
 extern "C" int fb_kth_table(int value, int k)
 {

@@ -61,6 +61,8 @@ def test_fast_legal_and_flips_match_oracle(fb, oracle):
         assert np.array_equal(out, want)
         fb.fb_flips_lut(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))         # all four lines by look-up
         assert np.array_equal(out, want)
+        fb.fb_flips_lut_line(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))    # ... diagonal masks by diagonal number (greedy kernel)
+        assert np.array_equal(out, want)
 
 
 def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
@@ -78,6 +80,8 @@ def test_constructed_lines_every_direction_square_and_run_length(fb, oracle):
     fb.fb_flips_rowlut(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
     assert np.array_equal(out, want)
     fb.fb_flips_lut(P(own), P(opp), P(sq), P(out), ctypes.c_long(n))
+    assert np.array_equal(out, want)
+    fb.fb_flips_lut_line(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))    # ... diagonal masks by diagonal number (greedy kernel)
     assert np.array_equal(out, want)
     assert (ret >= 6).sum() > 50 and (ret == 0).sum() > 1000          # six-disc runs and dead rays are both present
 
@@ -152,6 +156,8 @@ def test_rank_tables_every_rank_file_and_pattern(fb, oracle):
     assert own.size == 64 * 2187 and np.array_equal(out, want)
     fb.fb_flips_lut(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))
     assert np.array_equal(out, want)
+    fb.fb_flips_lut_line(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))    # ... diagonal masks by diagonal number (greedy kernel)
+    assert np.array_equal(out, want)
 
 
 def test_kth_set_bit_table(fb):
@@ -195,3 +201,6 @@ def test_line_tables_every_square_line_and_pattern(fb, oracle):
     fb.fb_flips_lut(P(own), P(opp), P(sq), P(out), ctypes.c_long(own.size))
     _, _, want, _ = oracle.put(own, opp, 1, sq)
     assert np.array_equal(out, want)
+    out2 = np.zeros(own.size, dtype=np.uint64)
+    fb.fb_flips_lut_line(P(own), P(opp), P(sq), P(out2), ctypes.c_long(own.size))    # diagonal masks by diagonal number
+    assert np.array_equal(out2, want)
