@@ -115,7 +115,7 @@ struct alignas(16) RayTableInit {
 static __device__ const RayTableInit kRayTable = RayTableInit();
 
 // N = obf::kRayBasic64: the ray masks of the carry-chain put() (2.5 KB); obf::kRayTable64: + the line look-up
-// tables of the game kernels (11.9 KB)
+// tables of the game kernels (12.2 KB)
 template <int N = obf::kRayBasic64>
 __device__ __forceinline__ void fill_rays(u64 *t)
 {
