@@ -44,6 +44,8 @@ def test_b200_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 131072 * 16 and e["d2h_bytes_per_step"] == 131072 * 2 + 32
     assert e["results_checked"] is True
+    assert e["standard_opening"]["value"] > 0 and e["standard_opening"]["h2d_bytes_per_step"] == 0
+    assert e["full_results"]["d2h_bytes_per_step"] == 131072 * 20 + 32
     # (chunked launches on rotating streams hide the tail of one launch behind the next: e2e may edge past `value`)
     assert e["value"] <= d["value"] * 1.15
     c4, c5 = d["extra"]["config4"], d["extra"]["config5"]
