@@ -420,6 +420,33 @@ def config5_extra(dev, rank, world, G=1 << 16, iters=10, warm=3, random_plies=10
                    "(progress_position_moves_learn.py:66-86,160-184) -- that path is subproc_b200.value_table"}
 
 
+def config5_table_extra(dev, G=1 << 16, iters=3, warm=1, random_plies=10):
+    """The same iteration with the REFERENCE's learning semantics (single GPU): every (position, side) of the greedy
+    games smooths the order-dependent value table in the reference's update order
+    (progress_position_moves_learn.py:37-62), then each shard is refitted on <= 50 000 distinct sampled table entries
+    (:66-86,160-184) and stored with int() truncation (:196-209).  Wall clock, synchronised per iteration."""
+    import torch
+    from subproc_b200 import learner
+    L = learner.ProgressPositionMovesLearn()
+    L.configure({})
+    times, nsamples, params = [], None, None
+    for it in range(warm + iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _po, (_mses, _scores, params, nsamples) = L.self_play_iteration_table(G, seed=5, iteration=it,
+                                                                           random_plies=random_plies, device=dev)
+        torch.cuda.synchronize()
+        if it >= warm:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * min(times)
+    return {"workload": "config5 with the reference's value-table semantics, one GPU", "games_per_iteration": G,
+            "iterations": iters, "iteration_ms": ms, "games_per_s": G / (ms * 1e-3), "table_keys": len(L.table),
+            "samples_per_shard": [int(v) for v in nsamples], "parameters": [int(v) for v in L.read_parameters()[1:]],
+            "what": "greedy self-play -> (key, target) records in update order -> stable radix sort -> runs of equal keys "
+                    "folded sequentially into the hash table in HBM (V = new if V == 0 else V * 0.97 + new * 0.03, fp64, "
+                    "bit-identical to the reference loop) -> four fits on sampled table entries"}
+
+
 def run_b200_arm(args):
     import ctypes
     import torch
@@ -610,6 +637,8 @@ def run_b200_arm(args):
     if not args.no_extra:
         extra["config4"] = config4_extra(dev, rank, world)
         extra["config5"] = config5_extra(dev, rank, world)
+        if world == 1:
+            extra["config5_table"] = config5_table_extra(dev)
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     if world > 1:

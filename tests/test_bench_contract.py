@@ -53,5 +53,7 @@ def test_b200_arm_line():
     assert c5["parity"] == {"allreduced_accumulators_equal_rank0_replay_of_all_game_ids": True,
                             "parameters_identical_on_all_ranks": True}
     assert c5["allreduce_bytes"] == 2560 and len(c5["parameters"]) == 36
+    c5t = d["extra"]["config5_table"]                          # the reference's value-table semantics
+    assert c5t["iteration_ms"] > 0 and c5t["table_keys"] > 0 and len(c5t["parameters"]) == 36
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
     assert d["clocks"]["sm_mhz"] is None or d["clocks"]["sm_mhz"] > 500
